@@ -1,0 +1,575 @@
+// api.cu — the extern "C" boundary (include/canny_b200.h): context, workspace pool, Gaussian tables,
+// stage entry points on host buffers, batched device/host pipelines.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "canny_math.h"
+#include "internal.h"
+
+namespace cb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ---- Gaussian weights: the reference's host code, expression for expression (src/utils.cpp:77-95) ----
+int host_window(float sigma) {
+    const float t = 3 * sigma;            // float product
+    return (int)(1 + 2 * ceilf(t));       // std::ceil(float) -> float; 1 + 2*c in float; truncation to int
+}
+void host_gaussian_kernel(float sigma, std::vector<float>& w) {
+    const int n = host_window(sigma);
+    const int mid = n / 2;
+    w.assign((size_t)n, 0.f);
+    float total = 0.0f;
+    for (int i = 0; i < n; i++) {
+        const float x = (float)(i - mid);
+        const float e = expf(-((x * x) / (2 * sigma * sigma)));  // std::exp(float)
+        const float pr = (float)((double)e / (sqrt(6.2831853) * (double)sigma));
+        w[(size_t)i] = pr;
+        total += pr;
+    }
+    for (int i = 0; i < n; i++) w[(size_t)i] /= total;
+}
+
+int ensure_ws(Workspace& ws, size_t bytes, bool pinned_host) {
+    if (ws.bytes >= bytes && ws.ptr) return B200_OK;
+    if (ws.ptr) {
+        if (pinned_host) cudaFreeHost(ws.ptr); else cudaFree(ws.ptr);
+        ws.ptr = nullptr;
+        ws.bytes = 0;
+    }
+    const size_t want = bytes + bytes / 8 + 256;  // slack so slowly growing requests do not realloc each time
+    cudaError_t e = pinned_host ? cudaMallocHost(&ws.ptr, want) : cudaMalloc(&ws.ptr, want);
+    if (e != cudaSuccess) {
+        ws.ptr = nullptr;
+        set_error("workspace allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+        cudaGetLastError();
+        return B200_ERR_NOMEM;
+    }
+    ws.bytes = want;
+    return B200_OK;
+}
+
+// Builds (or reuses) the weight / count / reciprocal tables for `sigma` and uploads them.
+int prepare_gauss(b200_ctx* ctx, float sigma) {
+    GaussTables& g = ctx->gauss;
+    if (g.sigma == sigma && g.d_w) return B200_OK;
+    if (!(sigma > 0.f) || !isfinite(sigma)) {
+        set_error("sigma must be a finite positive float (got %g)", (double)sigma);
+        return B200_ERR_INVALID_ARG;
+    }
+    const int window = host_window(sigma);
+    const int radius = window / 2;
+    if (radius < 1 || radius > B200_MAX_RADIUS) {
+        set_error("sigma %g gives window %d; supported half-window is 1..%d", (double)sigma, window, B200_MAX_RADIUS);
+        return B200_ERR_UNSUPPORTED;
+    }
+    host_gaussian_kernel(sigma, g.w);
+    const int n1 = radius + 1;
+    g.count.assign((size_t)2 * n1 * n1, 0.f);
+    for (int a = 0; a <= radius; ++a) {
+        for (int b = 0; b <= radius; ++b) {
+            float c = 0.f;  // `count += kernel[center+k]` over the in-image taps, ascending (src/utils.cpp:44,59)
+            for (int t = a; t <= 2 * radius - b; ++t) c += g.w[(size_t)t];
+            g.count[(size_t)a * n1 + b] = c;
+            // RN(1/c): the double quotient rounds to the same float as an exact one (53 >= 2*24+2 bits)
+            g.count[(size_t)n1 * n1 + (size_t)a * n1 + b] = (c != 0.f) ? (float)(1.0 / (double)c) : 0.f;
+        }
+    }
+    // one device allocation for both tables, sized for the largest radius so it is made once
+    if (!g.d_w) {
+        const size_t cap = sizeof(float) * ((2 * B200_MAX_RADIUS + 1) + 2 * (B200_MAX_RADIUS + 1) * (B200_MAX_RADIUS + 1));
+        CB_CUDA(cudaMalloc(reinterpret_cast<void**>(&g.d_w), cap));
+        g.d_count = g.d_w + (2 * B200_MAX_RADIUS + 1);
+    }
+    // the tables may still be in use by kernels of a previous sigma: order the upload after them
+    CB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int s = 0; s < 3; ++s) CB_CUDA(cudaStreamSynchronize(ctx->side[s]));
+    CB_CUDA(cudaMemcpyAsync(g.d_w, g.w.data(), sizeof(float) * g.w.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CB_CUDA(cudaMemcpyAsync(g.d_count, g.count.data(), sizeof(float) * g.count.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CB_CUDA(cudaStreamSynchronize(ctx->stream));
+    g.sigma = sigma;
+    g.window = window;
+    g.radius = radius;
+    return B200_OK;
+}
+
+static std::mutex g_default_mu;
+static b200_ctx* g_default_ctx = nullptr;
+
+static int resolve_ctx(b200_ctx*& ctx) {
+    if (ctx) {
+        CB_CUDA(cudaSetDevice(ctx->device));
+        return B200_OK;
+    }
+    std::lock_guard<std::mutex> lk(g_default_mu);
+    if (!g_default_ctx) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("no CUDA device available (libcanny_b200 has no CPU fallback)");
+            return B200_ERR_NO_DEVICE;
+        }
+        CB_TRY(b200_ctx_create(dev, &g_default_ctx));
+    }
+    ctx = g_default_ctx;
+    CB_CUDA(cudaSetDevice(ctx->device));
+    return B200_OK;
+}
+
+static int check_image(const void* in, const void* out, int h, int w) {
+    if (!in || !out) { set_error("null image pointer"); return B200_ERR_INVALID_ARG; }
+    if (h < 2 || w < 2) { set_error("height and width must be >= 2 (got %dx%d)", h, w); return B200_ERR_INVALID_ARG; }
+    if ((long long)h * w >= (1LL << 31)) { set_error("image of %dx%d pixels exceeds int indexing", h, w); return B200_ERR_UNSUPPORTED; }
+    return B200_OK;
+}
+
+static void fill_thresholds(FrontParams& p, int lo, int hi) {
+    // class of a kept pixel with squared magnitude n: candidate iff mag >= lo  <=>  n >= lo^2 (lo > 0), always if lo <= 0
+    const long long kBig = 0x7fffffff;
+    auto sq = [&](int v) -> int { if (v <= 0) return 0; long long s = (long long)v * v; return (int)std::min(s, kBig); };
+    p.lo = lo; p.hi = hi;
+    p.lo2 = sq(lo);
+    p.hi2 = sq(hi);
+    p.cls_zero = (0 >= lo) ? ((0 >= hi) ? 255 : 1) : 0;  // what a suppressed pixel (value 0) is: src/utils.cpp:328-333
+}
+
+// Runs front + hysteresis on device-resident frames [f0, f0+nf) using workspace slot `slot` on stream st.
+static int run_frames_device(b200_ctx* ctx, cudaStream_t st, int slot, const uint8_t* d_in, uint8_t* d_out, int nf, int h,
+                             int w, int lo, int hi, int16_t* blur, int16_t* mag, int16_t* ang, int16_t* nms) {
+    const long long px = (long long)h * w;
+    FrontParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.in = d_in; fp.in_frame_stride = px; fp.in_row0 = 0; fp.in_rows = h; fp.width = w; fp.height = h;
+    fp.out_row0 = 0; fp.out_rows = h; fp.n_frames = nf; fp.cls = d_out; fp.out_frame_stride = px;
+    fp.blur = blur; fp.mag = mag; fp.ang = ang; fp.nms = nms;
+    fp.w = ctx->gauss.d_w; fp.count = ctx->gauss.d_count; fp.radius = ctx->gauss.radius;
+    fill_thresholds(fp, lo, hi);
+    CB_TRY(launch_front(ctx, st, fp));
+    HystParams hp;
+    memset(&hp, 0, sizeof(hp));
+    hp.cls = d_out;
+    hp.parent = reinterpret_cast<int32_t*>(ctx->ws_parent[slot].ptr);
+    hp.frame_stride = px; hp.rows = h; hp.width = w; hp.row0 = 0; hp.n_frames = nf;
+    CB_TRY(launch_hysteresis(ctx, st, hp));
+    return B200_OK;
+}
+
+static int auto_chunk_frames(const b200_ctx* ctx, int h, int w, int n_frames) {
+    if (ctx->chunk_frames > 0) return std::min(ctx->chunk_frames, n_frames);
+    const long long px = (long long)h * w;
+    long long f = (32LL << 20) / px;  // ~32 Mpix per chunk: class map + touched labels stay L2 resident
+    if (f < 1) f = 1;
+    return (int)std::min<long long>(f, n_frames);
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+// =====================================================================================================
+extern "C" {
+
+int b200_version(void) { return 1; }
+const char* b200_last_error(void) { return g_err; }
+
+int b200_ctx_create(int device, b200_ctx** out) {
+    if (!out) { set_error("null out pointer"); return B200_ERR_INVALID_ARG; }
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (libcanny_b200 has no CPU fallback)");
+        return B200_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) { set_error("device %d out of range (have %d)", device, n); return B200_ERR_INVALID_ARG; }
+    cudaDeviceProp prop;
+    CB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; this library ships sm_100a code only", device, prop.major, prop.minor);
+        return B200_ERR_NO_DEVICE;
+    }
+    CB_CUDA(cudaSetDevice(device));
+    b200_ctx* c = new b200_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    CB_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    for (int i = 0; i < 3; ++i) {
+        CB_CUDA(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
+        CB_CUDA(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+    }
+    CB_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    *out = c;
+    return B200_OK;
+}
+
+int b200_ctx_destroy(b200_ctx* c) {
+    if (!c) return B200_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    auto rel = [](Workspace& w, bool pinned) { if (w.ptr) { if (pinned) cudaFreeHost(w.ptr); else cudaFree(w.ptr); w.ptr = nullptr; w.bytes = 0; } };
+    for (int i = 0; i < 3; ++i) { rel(c->ws_parent[i], false); rel(c->dev_in[i], false); rel(c->dev_out[i], false); }
+    rel(c->ws_planes, false); rel(c->ws_misc, false); rel(c->ws_band_parent, false);
+    if (c->gauss.d_w) cudaFree(c->gauss.d_w);
+    for (int i = 0; i < 3; ++i) { if (c->side[i]) cudaStreamDestroy(c->side[i]); if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]); }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    {
+        std::lock_guard<std::mutex> lk(g_default_mu);
+        if (g_default_ctx == c) g_default_ctx = nullptr;
+    }
+    delete c;
+    return B200_OK;
+}
+
+int b200_ctx_set_stream(b200_ctx* ctx, void* cuda_stream) {
+    CB_TRY(resolve_ctx(ctx));
+    ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return B200_OK;
+}
+int b200_ctx_synchronize(b200_ctx* ctx) {
+    CB_TRY(resolve_ctx(ctx));
+    CB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 3; ++i) CB_CUDA(cudaStreamSynchronize(ctx->side[i]));
+    return B200_OK;
+}
+int b200_ctx_set_chunk_frames(b200_ctx* ctx, int frames) {
+    CB_TRY(resolve_ctx(ctx));
+    ctx->chunk_frames = frames < 0 ? 0 : frames;
+    return B200_OK;
+}
+long long b200_ctx_kernel_launches(const b200_ctx* ctx) {
+    if (!ctx) ctx = g_default_ctx;
+    return ctx ? ctx->launches : 0;
+}
+
+// ---- host-side helpers ------------------------------------------------------------------------------
+int b200_gaussian_window(float sigma) { return host_window(sigma); }
+int b200_gaussian_kernel(float sigma, float* w, int* window) {
+    if (!w || !window || !(sigma > 0.f) || !isfinite(sigma)) { set_error("bad argument to b200_gaussian_kernel"); return B200_ERR_INVALID_ARG; }
+    std::vector<float> k;
+    host_gaussian_kernel(sigma, k);
+    memcpy(w, k.data(), sizeof(float) * k.size());
+    *window = (int)k.size();
+    return B200_OK;
+}
+int b200_direction_host(int gx, int gy) { return dir_code_to_angle(direction_code<long long>(gx, gy)); }
+int b200_isqrt_host(int n) { return isqrt_floor_host(n); }
+
+// ---- stage API on host buffers ------------------------------------------------------------------------
+// Scratch layout in ws_planes for one frame of px pixels: [u8 in | u8 cls | i16 a | i16 b | i16 c | i16 d | i16 e]
+struct Planes {
+    uint8_t *in, *cls;
+    int16_t* p16[5];
+};
+static int get_planes(b200_ctx* ctx, long long px, Planes& pl) {
+    const size_t pxa = ((size_t)px + 255) & ~(size_t)255;
+    CB_TRY(ensure_ws(ctx->ws_planes, pxa * 2 + pxa * 2 * 5));
+    uint8_t* base = reinterpret_cast<uint8_t*>(ctx->ws_planes.ptr);
+    pl.in = base;
+    pl.cls = base + pxa;
+    for (int i = 0; i < 5; ++i) pl.p16[i] = reinterpret_cast<int16_t*>(base + 2 * pxa + (size_t)i * 2 * pxa);
+    return B200_OK;
+}
+
+int b200_gaussian(b200_ctx* ctx, const uint8_t* img, float sigma, int h, int w, int16_t* blur) {
+    CB_TRY(check_image(img, blur, h, w));
+    CB_TRY(resolve_ctx(ctx));
+    CB_TRY(prepare_gauss(ctx, sigma));
+    const long long px = (long long)h * w;
+    Planes pl;
+    CB_TRY(get_planes(ctx, px, pl));
+    cudaStream_t st = ctx->stream;
+    CB_CUDA(cudaMemcpyAsync(pl.in, img, (size_t)px, cudaMemcpyHostToDevice, st));
+    FrontParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.in = pl.in; fp.in_frame_stride = px; fp.in_rows = h; fp.width = w; fp.height = h; fp.out_rows = h; fp.n_frames = 1;
+    fp.cls = pl.cls; fp.out_frame_stride = px; fp.blur = pl.p16[0];
+    fp.w = ctx->gauss.d_w; fp.count = ctx->gauss.d_count; fp.radius = ctx->gauss.radius;
+    fill_thresholds(fp, 1 << 20, 1 << 20);  // nothing is a candidate: the later phases do the minimum
+    CB_TRY(launch_front(ctx, st, fp));
+    CB_CUDA(cudaMemcpyAsync(blur, pl.p16[0], (size_t)px * 2, cudaMemcpyDeviceToHost, st));
+    CB_CUDA(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+int b200_xy_gradient(b200_ctx* ctx, const int16_t* blur, int h, int w, int16_t* gx, int16_t* gy) {
+    CB_TRY(check_image(blur, gx, h, w));
+    if (!gy) { set_error("null grad_y"); return B200_ERR_INVALID_ARG; }
+    CB_TRY(resolve_ctx(ctx));
+    const long long px = (long long)h * w;
+    Planes pl;
+    CB_TRY(get_planes(ctx, px, pl));
+    cudaStream_t st = ctx->stream;
+    CB_CUDA(cudaMemcpyAsync(pl.p16[0], blur, (size_t)px * 2, cudaMemcpyHostToDevice, st));
+    CB_TRY(launch_xy_gradient(ctx, st, pl.p16[0], h, w, pl.p16[1], pl.p16[2]));
+    CB_CUDA(cudaMemcpyAsync(gx, pl.p16[1], (size_t)px * 2, cudaMemcpyDeviceToHost, st));
+    CB_CUDA(cudaMemcpyAsync(gy, pl.p16[2], (size_t)px * 2, cudaMemcpyDeviceToHost, st));
+    CB_CUDA(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+int b200_sobel(b200_ctx* ctx, const int16_t* blur, int h, int w, int16_t* magnitude, int16_t* angle) {
+    CB_TRY(check_image(blur, magnitude, h, w));
+    if (!angle) { set_error("null angle"); return B200_ERR_INVALID_ARG; }
+    CB_TRY(resolve_ctx(ctx));
+    const long long px = (long long)h * w;
+    Planes pl;
+    CB_TRY(get_planes(ctx, px, pl));
+    cudaStream_t st = ctx->stream;
+    CB_CUDA(cudaMemcpyAsync(pl.p16[0], blur, (size_t)px * 2, cudaMemcpyHostToDevice, st));
+    CB_TRY(launch_sobel(ctx, st, pl.p16[0], h, w, pl.p16[1], pl.p16[2]));
+    CB_CUDA(cudaMemcpyAsync(magnitude, pl.p16[1], (size_t)px * 2, cudaMemcpyDeviceToHost, st));
+    CB_CUDA(cudaMemcpyAsync(angle, pl.p16[2], (size_t)px * 2, cudaMemcpyDeviceToHost, st));
+    CB_CUDA(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+int b200_nonmaximal(b200_ctx* ctx, const int16_t* magnitude, const int16_t* angle, int h, int w, int16_t* nms) {
+    CB_TRY(check_image(magnitude, nms, h, w));
+    if (!angle) { set_error("null angle"); return B200_ERR_INVALID_ARG; }
+    CB_TRY(resolve_ctx(ctx));
+    const long long px = (long long)h * w;
+    Planes pl;
+    CB_TRY(get_planes(ctx, px, pl));
+    cudaStream_t st = ctx->stream;
+    CB_CUDA(cudaMemcpyAsync(pl.p16[0], magnitude, (size_t)px * 2, cudaMemcpyHostToDevice, st));
+    CB_CUDA(cudaMemcpyAsync(pl.p16[1], angle, (size_t)px * 2, cudaMemcpyHostToDevice, st));
+    CB_TRY(launch_nonmaximal(ctx, st, pl.p16[0], pl.p16[1], h, w, pl.p16[2]));
+    CB_CUDA(cudaMemcpyAsync(nms, pl.p16[2], (size_t)px * 2, cudaMemcpyDeviceToHost, st));
+    CB_CUDA(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+int b200_hysteresis(b200_ctx* ctx, int16_t* nms_inout, int h, int w, int lo, int hi) {
+    CB_TRY(check_image(nms_inout, nms_inout, h, w));
+    CB_TRY(resolve_ctx(ctx));
+    const long long px = (long long)h * w;
+    Planes pl;
+    CB_TRY(get_planes(ctx, px, pl));
+    CB_TRY(ensure_ws(ctx->ws_parent[0], (size_t)px * 4));
+    cudaStream_t st = ctx->stream;
+    CB_CUDA(cudaMemcpyAsync(pl.p16[0], nms_inout, (size_t)px * 2, cudaMemcpyHostToDevice, st));
+    CB_TRY(launch_classify_i16(ctx, st, pl.p16[0], pl.cls, (size_t)px, lo, hi));
+    HystParams hp;
+    memset(&hp, 0, sizeof(hp));
+    hp.cls = pl.cls; hp.parent = reinterpret_cast<int32_t*>(ctx->ws_parent[0].ptr);
+    hp.frame_stride = px; hp.rows = h; hp.width = w; hp.row0 = 0; hp.n_frames = 1;
+    CB_TRY(launch_hysteresis(ctx, st, hp));
+    CB_TRY(launch_expand_u8_to_i16(ctx, st, pl.cls, pl.p16[1], (size_t)px));
+    CB_CUDA(cudaMemcpyAsync(nms_inout, pl.p16[1], (size_t)px * 2, cudaMemcpyDeviceToHost, st));
+    CB_CUDA(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+int b200_canny_steps(b200_ctx* ctx, const uint8_t* img, float sigma, int lo, int hi, int h, int w, int16_t* blur,
+                     int16_t* magnitude, int16_t* angle, int16_t* nms, int16_t* edges) {
+    CB_TRY(check_image(img, edges, h, w));
+    CB_TRY(resolve_ctx(ctx));
+    CB_TRY(prepare_gauss(ctx, sigma));
+    const long long px = (long long)h * w;
+    Planes pl;
+    CB_TRY(get_planes(ctx, px, pl));
+    CB_TRY(ensure_ws(ctx->ws_parent[0], (size_t)px * 4));
+    cudaStream_t st = ctx->stream;
+    CB_CUDA(cudaMemcpyAsync(pl.in, img, (size_t)px, cudaMemcpyHostToDevice, st));
+    CB_TRY(run_frames_device(ctx, st, 0, pl.in, pl.cls, 1, h, w, lo, hi, blur ? pl.p16[0] : nullptr,
+                             magnitude ? pl.p16[1] : nullptr, angle ? pl.p16[2] : nullptr, nms ? pl.p16[3] : nullptr));
+    CB_TRY(launch_expand_u8_to_i16(ctx, st, pl.cls, pl.p16[4], (size_t)px));
+    if (blur) CB_CUDA(cudaMemcpyAsync(blur, pl.p16[0], (size_t)px * 2, cudaMemcpyDeviceToHost, st));
+    if (magnitude) CB_CUDA(cudaMemcpyAsync(magnitude, pl.p16[1], (size_t)px * 2, cudaMemcpyDeviceToHost, st));
+    if (angle) CB_CUDA(cudaMemcpyAsync(angle, pl.p16[2], (size_t)px * 2, cudaMemcpyDeviceToHost, st));
+    if (nms) CB_CUDA(cudaMemcpyAsync(nms, pl.p16[3], (size_t)px * 2, cudaMemcpyDeviceToHost, st));
+    CB_CUDA(cudaMemcpyAsync(edges, pl.p16[4], (size_t)px * 2, cudaMemcpyDeviceToHost, st));
+    CB_CUDA(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+int b200_canny(b200_ctx* ctx, const uint8_t* img, float sigma, int lo, int hi, int h, int w, int16_t* edges) {
+    return b200_canny_steps(ctx, img, sigma, lo, hi, h, w, nullptr, nullptr, nullptr, nullptr, edges);
+}
+
+// ---- batched --------------------------------------------------------------------------------------------
+int b200_canny_batch_device(b200_ctx* ctx, const uint8_t* d_frames, int n_frames, int h, int w, float sigma, int lo,
+                            int hi, uint8_t* d_edges) {
+    CB_TRY(check_image(d_frames, d_edges, h, w));
+    if (n_frames <= 0) { set_error("n_frames must be positive"); return B200_ERR_INVALID_ARG; }
+    CB_TRY(resolve_ctx(ctx));
+    CB_TRY(prepare_gauss(ctx, sigma));
+    const long long px = (long long)h * w;
+    const int chunk = auto_chunk_frames(ctx, h, w, n_frames);
+    const int n_chunks = (n_frames + chunk - 1) / chunk;
+    const int n_slots = n_chunks >= 2 ? 2 : 1;
+    for (int s = 0; s < n_slots; ++s) CB_TRY(ensure_ws(ctx->ws_parent[s], (size_t)px * 4 * (size_t)chunk));
+    if (n_slots == 1) {
+        CB_TRY(run_frames_device(ctx, ctx->stream, 0, d_frames, d_edges, n_frames, h, w, lo, hi, nullptr, nullptr, nullptr, nullptr));
+        return B200_OK;
+    }
+    // two side streams take alternate chunks so one chunk's tail waves overlap the next chunk's head
+    CB_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    for (int s = 0; s < n_slots; ++s) CB_CUDA(cudaStreamWaitEvent(ctx->side[s], ctx->ev_fork, 0));
+    for (int c = 0; c < n_chunks; ++c) {
+        const int f0 = c * chunk, nf = std::min(chunk, n_frames - f0);
+        const int s = c % n_slots;
+        CB_TRY(run_frames_device(ctx, ctx->side[s], s, d_frames + (long long)f0 * px, d_edges + (long long)f0 * px, nf, h, w, lo,
+                                 hi, nullptr, nullptr, nullptr, nullptr));
+    }
+    for (int s = 0; s < n_slots; ++s) {
+        CB_CUDA(cudaEventRecord(ctx->ev_join[s], ctx->side[s]));
+        CB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[s], 0));
+    }
+    return B200_OK;
+}
+
+int b200_canny_batch_host(b200_ctx* ctx, const uint8_t* frames, int n_frames, int h, int w, float sigma, int lo, int hi,
+                          uint8_t* edges) {
+    CB_TRY(check_image(frames, edges, h, w));
+    if (n_frames <= 0) { set_error("n_frames must be positive"); return B200_ERR_INVALID_ARG; }
+    CB_TRY(resolve_ctx(ctx));
+    CB_TRY(prepare_gauss(ctx, sigma));
+    const long long px = (long long)h * w;
+    // chunks of ~64 MB: big enough for full PCIe rate, small enough that three are in flight (H2D | kernels | D2H)
+    int chunk = ctx->chunk_frames > 0 ? ctx->chunk_frames : (int)std::max<long long>(1, (64LL << 20) / px);
+    chunk = std::min(chunk, n_frames);
+    const int n_chunks = (n_frames + chunk - 1) / chunk;
+    const int n_slots = std::min(3, n_chunks);
+    for (int s = 0; s < n_slots; ++s) {
+        CB_TRY(ensure_ws(ctx->ws_parent[s], (size_t)px * 4 * (size_t)chunk));
+        CB_TRY(ensure_ws(ctx->dev_in[s], (size_t)px * (size_t)chunk));
+        CB_TRY(ensure_ws(ctx->dev_out[s], (size_t)px * (size_t)chunk));
+    }
+    CB_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    for (int s = 0; s < n_slots; ++s) CB_CUDA(cudaStreamWaitEvent(ctx->side[s], ctx->ev_fork, 0));
+    for (int c = 0; c < n_chunks; ++c) {
+        const int f0 = c * chunk, nf = std::min(chunk, n_frames - f0);
+        const int s = c % n_slots;
+        cudaStream_t st = ctx->side[s];
+        uint8_t* din = reinterpret_cast<uint8_t*>(ctx->dev_in[s].ptr);
+        uint8_t* dout = reinterpret_cast<uint8_t*>(ctx->dev_out[s].ptr);
+        // stream order on `st` makes slot reuse safe: chunk c+n_slots' H2D waits for chunk c's D2H
+        CB_CUDA(cudaMemcpyAsync(din, frames + (long long)f0 * px, (size_t)px * nf, cudaMemcpyHostToDevice, st));
+        CB_TRY(run_frames_device(ctx, st, s, din, dout, nf, h, w, lo, hi, nullptr, nullptr, nullptr, nullptr));
+        CB_CUDA(cudaMemcpyAsync(edges + (long long)f0 * px, dout, (size_t)px * nf, cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < n_slots; ++s) {
+        CB_CUDA(cudaEventRecord(ctx->ev_join[s], ctx->side[s]));
+        CB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[s], 0));
+    }
+    CB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+
+int b200_profile_stages_device(b200_ctx* ctx, const uint8_t* d_frames, int n_frames, int h, int w, float sigma, int lo, int hi,
+                               uint8_t* d_edges, float* ms_out, int* launches_out) {
+    CB_TRY(check_image(d_frames, d_edges, h, w));
+    if (!ms_out || !launches_out || n_frames <= 0) { set_error("bad argument"); return B200_ERR_INVALID_ARG; }
+    CB_TRY(resolve_ctx(ctx));
+    CB_TRY(prepare_gauss(ctx, sigma));
+    const long long px = (long long)h * w;
+    const int chunk = auto_chunk_frames(ctx, h, w, n_frames);
+    CB_TRY(ensure_ws(ctx->ws_parent[0], (size_t)px * 4 * (size_t)chunk));
+    CB_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->prof.recs.clear();
+    ctx->prof.on = true;
+    int status = B200_OK;
+    for (int f0 = 0; f0 < n_frames && status == B200_OK; f0 += chunk) {
+        const int nf = std::min(chunk, n_frames - f0);
+        status = run_frames_device(ctx, ctx->stream, 0, d_frames + (long long)f0 * px, d_edges + (long long)f0 * px, nf, h, w, lo, hi,
+                                   nullptr, nullptr, nullptr, nullptr);
+    }
+    ctx->prof.on = false;
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    for (int c = 0; c < 5; ++c) { ms_out[c] = 0.f; launches_out[c] = 0; }
+    for (auto& r : ctx->prof.recs) {
+        float ms = 0.f;
+        if (e == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { ms_out[r.cat] += ms; launches_out[r.cat]++; }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    ctx->prof.recs.clear();
+    if (e != cudaSuccess) { set_error("profile run failed: %s", cudaGetErrorString(e)); return B200_ERR_CUDA; }
+    return status;
+}
+
+// ---- synthetic workloads / helpers -------------------------------------------------------------------------
+int b200_synth_rows_host(uint8_t* out, int row0, int rows, int width, int kind, uint64_t seed, int frame) {
+    if (!out || rows < 0 || width <= 0) { set_error("bad argument to b200_synth_rows_host"); return B200_ERR_INVALID_ARG; }
+    for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < width; ++c) out[(size_t)r * width + c] = synth_pixel(kind, seed, frame, c, row0 + r);
+    return B200_OK;
+}
+int b200_synth_host(uint8_t* frames, int n_frames, int h, int w, int kind, uint64_t seed, int first_frame) {
+    if (!frames || n_frames < 0) { set_error("bad argument to b200_synth_host"); return B200_ERR_INVALID_ARG; }
+    for (int f = 0; f < n_frames; ++f) CB_TRY(b200_synth_rows_host(frames + (size_t)f * h * w, 0, h, w, kind, seed, first_frame + f));
+    return B200_OK;
+}
+int b200_synth_rows_device(b200_ctx* ctx, uint8_t* d_rows, int row0, int rows, int width, int kind, uint64_t seed, int frame) {
+    if (!d_rows || rows <= 0 || width <= 0) { set_error("bad argument to b200_synth_rows_device"); return B200_ERR_INVALID_ARG; }
+    CB_TRY(resolve_ctx(ctx));
+    return launch_synth(ctx, ctx->stream, d_rows, 1, row0, rows, width, kind, seed, frame);
+}
+int b200_synth_device(b200_ctx* ctx, uint8_t* d_frames, int n_frames, int h, int w, int kind, uint64_t seed, int first_frame) {
+    if (!d_frames || n_frames <= 0 || h <= 0 || w <= 0) { set_error("bad argument to b200_synth_device"); return B200_ERR_INVALID_ARG; }
+    CB_TRY(resolve_ctx(ctx));
+    return launch_synth(ctx, ctx->stream, d_frames, n_frames, 0, h, w, kind, seed, first_frame);
+}
+
+int b200_count_edges_device(b200_ctx* ctx, const uint8_t* d_edges, size_t n, unsigned long long* count) {
+    if (!d_edges || !count) { set_error("null pointer"); return B200_ERR_INVALID_ARG; }
+    CB_TRY(resolve_ctx(ctx));
+    CB_TRY(ensure_ws(ctx->ws_misc, 256));
+    unsigned long long* d = reinterpret_cast<unsigned long long*>(ctx->ws_misc.ptr);
+    CB_TRY(launch_count255(ctx, ctx->stream, d_edges, n, d));
+    CB_CUDA(cudaMemcpyAsync(count, d, sizeof(*count), cudaMemcpyDeviceToHost, ctx->stream));
+    CB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+
+int b200_device_alloc(b200_ctx* ctx, size_t bytes, void** d_ptr) {
+    if (!d_ptr) { set_error("null pointer"); return B200_ERR_INVALID_ARG; }
+    CB_TRY(resolve_ctx(ctx));
+    cudaError_t e = cudaMalloc(d_ptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return B200_ERR_NOMEM; }
+    return B200_OK;
+}
+int b200_device_free(b200_ctx* ctx, void* d_ptr) {
+    CB_TRY(resolve_ctx(ctx));
+    CB_CUDA(cudaFree(d_ptr));
+    return B200_OK;
+}
+int b200_memcpy_h2d(b200_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+    CB_TRY(resolve_ctx(ctx));
+    CB_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+int b200_memcpy_d2h(b200_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+    CB_TRY(resolve_ctx(ctx));
+    CB_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+int b200_host_alloc_pinned(size_t bytes, void** h_ptr) {
+    if (!h_ptr) { set_error("null pointer"); return B200_ERR_INVALID_ARG; }
+    cudaError_t e = cudaMallocHost(h_ptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e)); return B200_ERR_NOMEM; }
+    return B200_OK;
+}
+int b200_host_free_pinned(void* h_ptr) {
+    CB_CUDA(cudaFreeHost(h_ptr));
+    return B200_OK;
+}
+
+}  // extern "C"

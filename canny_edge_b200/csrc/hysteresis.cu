@@ -1,0 +1,338 @@
+// hysteresis.cu — stage 4 as GPU connected components.
+//
+// Replaces hysteresis() + findEdgePixels() (src/utils.cpp:322-342, 360-427), which the reference runs on
+// the CPU even in its CUDA path (src/cuda.cu:436).  The reference floods breadth-first from every pixel
+// >= maxVal through 8-connected pixels >= minVal.  Equivalent formulation used here:
+//   candidates = class != 0, seeds = class 255; label the 8-connected components of the candidates with a
+//   union-find forest; a weak pixel survives iff its component contains a seed.
+// "Contains a seed" is folded into the forest itself: every component that holds a seed is linked under
+// one virtual root SUPER (-1, smaller than any pixel index, never stored as a slot), so the final test is
+// find(p) == SUPER and no separate flag propagation pass exists.
+//
+// The reference's single missing directed link (src/utils.cpp:399: `current - width > 0` is false for
+// current == width) means pixel (1,0) never reaches (0,1) although (0,1) reaches (1,0).  The edge
+// (0,1)-(1,0) is therefore left out of the forest and re-applied one-way in the final pass: if (0,1)'s
+// component is strong, (1,0)'s becomes strong; not the other way round.
+//
+// Kernels:
+//   ccl_local   one CTA per 64x64 tile: union-find in shared memory (atomicMin links, row-run seeding
+//               with warp ballots), then writes each candidate's parent (its tile root, or SUPER).
+//   ccl_merge   one thread per pixel on a tile boundary: lock-free atomicMin unions in global memory.
+//   ccl_final   every weak pixel chases its root; rewrites the class map to 0 / 255 in place.
+#include <string.h>
+
+#include "ccl.cuh"
+#include "internal.h"
+
+namespace cb {
+
+
+// ---------------------------------------------------------------------------------------------
+// kernel 1: tile-local labelling
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCclThreads)
+ccl_local_kernel(const HystParams p) {
+    __shared__ unsigned char s_cls[kTile][kTile + 16];
+    __shared__ int s_lab[kTile * kTile];
+    __shared__ unsigned char s_strong[kTile * kTile];
+    __shared__ int s_any;
+
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
+    const int frame = blockIdx.z;
+    const uint8_t* cls = p.cls + (long long)frame * p.frame_stride;
+    int32_t* parent = p.parent + (long long)frame * p.frame_stride;
+    const int W = p.width, Hh = p.rows;
+
+    if (tid == 0) s_any = 0;
+    __syncthreads();
+
+    // ---- load the tile (16 B per thread-iteration when aligned), remember whether it has any candidate ----
+    const bool vec_ok = ((W & 15) == 0) && ((reinterpret_cast<uintptr_t>(cls) & 15) == 0);
+    int any = 0;
+    for (int i = tid; i < kTile * (kTile / 16); i += kCclThreads) {
+        const int r = i >> 2, q = i & 3;
+        const int y = y0 + r, x = x0 + 16 * q;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (y < Hh) {
+            if (vec_ok && x + 15 < W) {
+                v = __ldg(reinterpret_cast<const uint4*>(cls + (long long)y * W + x));
+            } else {
+                unsigned char tmp[16];
+                for (int e = 0; e < 16; ++e) tmp[e] = (x + e < W) ? cls[(long long)y * W + x + e] : 0;
+                v = *reinterpret_cast<uint4*>(tmp);
+            }
+        }
+        *reinterpret_cast<uint4*>(&s_cls[r][16 * q]) = v;
+        any |= (v.x | v.y | v.z | v.w) != 0;
+    }
+    if (any) s_any = 1;
+    __syncthreads();
+    if (!s_any) return;  // nothing to label in this tile (the common case on sparse edge maps)
+
+    // ---- seed labels: every candidate starts at the head of its horizontal run ----
+    // warp w handles rows w, w+8, ...; lanes cover the 64 columns in two halves, run heads found with ballots
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int r = warp; r < kTile; r += kCclThreads / 32) {
+        const bool c_lo = s_cls[r][lane] != 0, c_hi = s_cls[r][32 + lane] != 0;
+        const unsigned m_lo = __ballot_sync(0xffffffffu, c_lo), m_hi = __ballot_sync(0xffffffffu, c_hi);
+        const unsigned long long m = ((unsigned long long)m_hi << 32) | m_lo;
+        // head of the run containing column c: one past the highest zero bit below c
+        {
+            const int c = lane;
+            int lab = -1;
+            if (c_lo) {
+                const unsigned long long below = ~m & ((1ull << c) - 1ull);
+                const int head = below ? (64 - __clzll(below)) : 0;
+                lab = r * kTile + head;
+            }
+            s_lab[r * kTile + c] = lab;
+            s_strong[r * kTile + c] = 0;
+        }
+        {
+            const int c = 32 + lane;
+            int lab = -1;
+            if (c_hi) {
+                const unsigned long long below = ~m & ((1ull << c) - 1ull);
+                const int head = below ? (64 - __clzll(below)) : 0;
+                lab = r * kTile + head;
+            }
+            s_lab[r * kTile + c] = lab;
+            s_strong[r * kTile + c] = 0;
+        }
+    }
+    __syncthreads();
+
+    // ---- vertical / diagonal unions: only run heads... every candidate whose upper neighbours are candidates ----
+    // (left neighbour is already in the same run).  The pair (1,0)-(0,1) of the GLOBAL image is skipped.
+    for (int i = tid; i < kTile * kTile; i += kCclThreads) {
+        const int r = i >> 6, c = i & 63;
+        if (r == 0 || s_cls[r][c] == 0) continue;
+        const bool up = s_cls[r - 1][c] != 0;
+        if (up) {
+            s_union(s_lab, i, i - kTile);
+        } else {
+            // with `up` set, the two diagonals are already joined to it through their own runs
+            if (c > 0 && s_cls[r - 1][c - 1] != 0) s_union(s_lab, i, i - kTile - 1);
+            if (c < kTile - 1 && s_cls[r - 1][c + 1] != 0) {
+                const bool quirk = (p.row0 + y0 + r == 1) && (x0 + c == 0);
+                if (!quirk) s_union(s_lab, i, i - kTile + 1);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- flatten + mark roots of components that contain a seed ----
+    for (int i = tid; i < kTile * kTile; i += kCclThreads) {
+        const int r = i >> 6, c = i & 63;
+        if (s_cls[r][c] == 0) continue;
+        const int root = s_find(s_lab, i);
+        s_lab[i] = root;
+        if (s_cls[r][c] == 255) s_strong[root] = 1;
+    }
+    __syncthreads();
+
+    // ---- publish: parent = tile root (as a frame-relative pixel index), or SUPER for the root of a strong component ----
+    for (int i = tid; i < kTile * kTile; i += kCclThreads) {
+        const int r = i >> 6, c = i & 63;
+        if (s_cls[r][c] == 0) continue;
+        const int root = s_lab[i];
+        const int gi = (y0 + r) * W + (x0 + c);
+        int val;
+        if (root == i) val = s_strong[i] ? kSuper : gi;
+        else val = (y0 + (root >> 6)) * W + (x0 + (root & 63));
+        parent[gi] = val;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel 2: unions across tile boundaries
+// ---------------------------------------------------------------------------------------------
+// work item space: [0, n_hb*W) horizontal boundaries (row 64i-1 | row 64i), then [.., + n_vb*H) vertical ones
+__global__ void __launch_bounds__(256)
+ccl_merge_kernel(const HystParams p) {
+    const int W = p.width, Hh = p.rows;
+    const int n_hb = p.tiles_y - 1, n_vb = p.tiles_x - 1;
+    const long long n_h = (long long)n_hb * W, n_v = (long long)n_vb * Hh;
+    const int frame = blockIdx.y;
+    const uint8_t* cls = p.cls + (long long)frame * p.frame_stride;
+    int32_t* parent = p.parent + (long long)frame * p.frame_stride;
+    for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < n_h + n_v;
+         it += (long long)gridDim.x * blockDim.x) {
+        if (it < n_h) {
+            const int b = (int)(it / W), x = (int)(it - (long long)b * W);
+            const int y = (b + 1) * kTile - 1;  // upper row of the boundary; y+1 < Hh because the tile below exists
+            const int a = y * W + x;
+            if (cls[a] == 0) continue;
+            const int below = a + W;
+            // (0,1)-(1,0), the one pair that must not be joined, never straddles a tile boundary (kTile > 1).
+            if (cls[below] != 0) {
+                // the two diagonals sit next to `below` in row y+1, so they reach `a` through it
+                g_union(parent, a, below);
+            } else {
+                if (x > 0 && cls[below - 1] != 0) g_union(parent, a, below - 1);
+                if (x < W - 1 && cls[below + 1] != 0) g_union(parent, a, below + 1);
+            }
+        } else {
+            const long long j = it - n_h;
+            const int b = (int)(j / Hh), y = (int)(j - (long long)b * Hh);
+            const int x = (b + 1) * kTile - 1;  // left column of the boundary; x+1 < W because the tile to the right exists
+            const int a = y * W + x;
+            if (cls[a] == 0) continue;
+            const int right = a + 1;
+            if (cls[right] != 0) {
+                g_union(parent, a, right);  // (y-1,x+1) and (y+1,x+1) are vertical neighbours of `right`
+            } else {
+                if (y > 0 && cls[right - W] != 0) g_union(parent, a, right - W);
+                if (y < Hh - 1 && cls[right + W] != 0) g_union(parent, a, right + W);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel 3: resolve weak pixels in place
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ccl_final_kernel(const HystParams p) {
+    __shared__ int s_qroot;
+    const int W = p.width, Hh = p.rows;
+    const int frame = blockIdx.y;
+    uint8_t* cls = p.cls + (long long)frame * p.frame_stride;
+    const int32_t* parent = p.parent + (long long)frame * p.frame_stride;
+
+    // the one-way link (0,1) -> (1,0) of the global image (see file header)
+    if (threadIdx.x == 0) {
+        int q = kNone;
+        if (p.row0 == 0 && Hh >= 2 && W >= 2 && cls[1] != 0 && cls[W] != 0) {
+            if (g_find(parent, 1) == kSuper) q = g_find(parent, W);
+        }
+        s_qroot = q;
+    }
+    __syncthreads();
+    const int qroot = s_qroot;
+
+    const long long n = (long long)Hh * W;
+    const bool vec_ok = ((n & 15) == 0) && ((reinterpret_cast<uintptr_t>(cls) & 15) == 0);
+    if (vec_ok) {
+        const long long n16 = n >> 4;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) {
+            uint4 v = *reinterpret_cast<const uint4*>(cls + 16 * i);
+            uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+            bool changed = false;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t w = wv[k];
+                // any byte == 1 ?  (bytes are 0, 1 or 255)
+                if (((w & 0x01010101u) & ~(w >> 1)) == 0) continue;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (((w >> (8 * e)) & 0xFF) == 1) {
+                        const int idx = (int)(16 * i + 4 * k + e);
+                        const int root = g_find(parent, idx);
+                        const uint32_t out = (root == kSuper || root == qroot) ? 255u : 0u;
+                        w = (w & ~(0xFFu << (8 * e))) | (out << (8 * e));
+                    }
+                }
+                wv[k] = w;
+                changed = true;
+            }
+            if (changed) *reinterpret_cast<uint4*>(cls + 16 * i) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+        }
+    } else {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+            if (cls[i] == 1) {
+                const int root = g_find(parent, (int)i);
+                cls[i] = (root == kSuper || root == qroot) ? 255 : 0;
+            }
+        }
+    }
+}
+
+int launch_ccl_label(b200_ctx* ctx, cudaStream_t st, const HystParams& p_in) {
+    HystParams p = p_in;
+    p.tiles_x = (p.width + kTile - 1) / kTile;
+    p.tiles_y = (p.rows + kTile - 1) / kTile;
+    {
+        dim3 grid(p.tiles_x, p.tiles_y, p.n_frames);
+        ProfScope ps(ctx, st, 1);
+        ccl_local_kernel<<<grid, kCclThreads, 0, st>>>(p);
+        CB_CUDA(cudaGetLastError());
+        ctx->launches++;
+    }
+    const long long items = (long long)(p.tiles_y - 1) * p.width + (long long)(p.tiles_x - 1) * p.rows;
+    if (items > 0) {
+        int blocks = (int)((items + 255) / 256);
+        if (blocks > 4096) blocks = 4096;
+        dim3 grid(blocks, p.n_frames);
+        {
+            ProfScope ps(ctx, st, 2);
+            ccl_merge_kernel<<<grid, 256, 0, st>>>(p);
+        }
+        CB_CUDA(cudaGetLastError());
+        ctx->launches++;
+    }
+    return B200_OK;
+}
+
+int launch_ccl_resolve(b200_ctx* ctx, cudaStream_t st, const HystParams& p_in) {
+    HystParams p = p_in;
+    p.tiles_x = (p.width + kTile - 1) / kTile;
+    p.tiles_y = (p.rows + kTile - 1) / kTile;
+    const long long n16 = ((long long)p.rows * p.width + 15) / 16;
+    int blocks = (int)((n16 + 255) / 256);
+    const int cap = 8 * (ctx->sm_count > 0 ? ctx->sm_count : 148);
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    dim3 grid(blocks, p.n_frames);
+    {
+        ProfScope ps(ctx, st, 3);
+        ccl_final_kernel<<<grid, 256, 0, st>>>(p);
+    }
+    CB_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return B200_OK;
+}
+
+int launch_hysteresis(b200_ctx* ctx, cudaStream_t st, const HystParams& p) {
+    CB_TRY(launch_ccl_label(ctx, st, p));
+    return launch_ccl_resolve(ctx, st, p);
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage-API helpers: int16 nms plane -> class map, class map -> int16 0/255
+// ---------------------------------------------------------------------------------------------
+__global__ void classify_i16_kernel(const int16_t* __restrict__ nms, uint8_t* __restrict__ cls, size_t n, int lo, int hi) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int v = nms[i];
+        // src/utils.cpp:328-333: below minVal -> dropped; otherwise >= maxVal seeds a flood
+        cls[i] = (v < lo) ? 0 : ((v >= hi) ? 255 : 1);
+    }
+}
+__global__ void expand_u8_i16_kernel(const uint8_t* __restrict__ cls, int16_t* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = cls[i];
+}
+
+static int grid_for(size_t n, const b200_ctx* ctx) {
+    size_t b = (n + 255) / 256;
+    size_t cap = 16 * (size_t)(ctx->sm_count > 0 ? ctx->sm_count : 148);
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+int launch_classify_i16(b200_ctx* ctx, cudaStream_t st, const int16_t* nms, uint8_t* cls, size_t n, int lo, int hi) {
+    classify_i16_kernel<<<grid_for(n, ctx), 256, 0, st>>>(nms, cls, n, lo, hi);
+    CB_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return B200_OK;
+}
+int launch_expand_u8_to_i16(b200_ctx* ctx, cudaStream_t st, const uint8_t* cls, int16_t* out, size_t n) {
+    expand_u8_i16_kernel<<<grid_for(n, ctx), 256, 0, st>>>(cls, out, n);
+    CB_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return B200_OK;
+}
+
+}  // namespace cb

@@ -1,0 +1,162 @@
+// internal.h — declarations shared between the translation units of libcanny_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/canny_b200.h"
+
+namespace cb {
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+#define CB_CUDA(expr)                                                                      \
+    do {                                                                                   \
+        cudaError_t e_ = (expr);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            cb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, \
+                          __LINE__);                                                       \
+            return B200_ERR_CUDA;                                                          \
+        }                                                                                  \
+    } while (0)
+#define CB_TRY(expr)                   \
+    do {                               \
+        int s_ = (expr);               \
+        if (s_ != B200_OK) return s_;  \
+    } while (0)
+
+// ---- Gaussian tables (host generated, bit-identical to the reference's float arithmetic) ------
+struct GaussTables {
+    float sigma = -1.f;
+    int window = 0, radius = 0;
+    std::vector<float> w;      // window weights, src/utils.cpp:77-95
+    std::vector<float> count;  // (radius+1)^2: count[a*(radius+1)+b] = sum of weights with the first a
+                               // and last b taps skipped, accumulated in ascending tap order
+                               // exactly as src/utils.cpp:44,59 do
+    float* d_w = nullptr;      // device copies (owned by the context)
+    float* d_count = nullptr;
+};
+
+// ---- parameters of the fused front kernel -----------------------------------------------------
+// The kernel works in GLOBAL image coordinates so the same code serves whole frames and row bands.
+struct FrontParams {
+    const uint8_t* in;      // first byte of buffer row 0 of frame 0
+    long long in_frame_stride;  // bytes between frames in `in`
+    int in_row0;            // global row index of buffer row 0 (0 for whole frames; row0-halo for bands)
+    int in_rows;            // rows present in the buffer
+    int width;              // image width == pitch of every plane
+    int height;             // GLOBAL image height (border rules key off this)
+    int out_row0;           // first global row this launch produces
+    int out_rows;           // number of rows produced (planes below are indexed from out_row0)
+    int n_frames;
+    uint8_t* cls;           // out: class map (0 / 1 weak / 255 strong), out_rows*width per frame
+    long long out_frame_stride;  // elements between frames in every output plane
+    int16_t* blur;          // optional spill planes (steps / stage API); may be null
+    int16_t* mag;
+    int16_t* ang;
+    int16_t* nms;
+    const float* w;         // device weights [2*radius+1]
+    const float* count;     // device count table [(radius+1)^2]
+    int radius;
+    int lo2, hi2;           // thresholds in squared-magnitude space (see front.cu)
+    int lo, hi;             // raw thresholds (spill / zero-class decisions)
+    int cls_zero;           // class of a suppressed pixel (value 0): nonzero only when lo <= 0
+    int tiles_x, tiles_y;
+};
+
+// ---- parameters of the hysteresis (connected components) kernels ---------------------------------
+struct HystParams {
+    uint8_t* cls;          // in/out: 0 / 1 / 255 -> 0 / 255   (rows*width per frame)
+    int32_t* parent;       // workspace: union-find parent per pixel (only candidate entries are defined)
+    long long frame_stride;  // elements between frames (cls and parent)
+    int rows, width;       // rows in this launch's plane (whole frame or band)
+    int row0;              // global row of plane row 0 (the missing-link quirk lives at global (1,0)->(0,1))
+    int n_frames;
+    int tiles_x, tiles_y;
+};
+
+// ---- the context ------------------------------------------------------------------------------
+struct Workspace {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace cb
+
+namespace cb {
+// Optional per-kernel timing (b200_profile_stages_device): every launch site brackets its kernel with two
+// events on the launching stream; categories: 0 front, 1 ccl_local, 2 ccl_merge, 3 ccl_final, 4 other.
+struct ProfRecord { int cat; cudaEvent_t a, b; };
+struct Profiler {
+    bool on = false;
+    std::vector<ProfRecord> recs;
+};
+}  // namespace cb
+
+struct b200_ctx {
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;   // private stream
+    cudaStream_t stream = nullptr;       // stream work is issued on (own_stream or the user's)
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};  // chunk pipelining / copy overlap
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+    cb::GaussTables gauss;
+    cb::Workspace ws_parent[3];   // int32 union-find slots for one chunk, per pipeline slot
+    cb::Workspace ws_planes;      // stage-API scratch planes
+    cb::Workspace ws_misc;
+    cb::Workspace dev_in[3], dev_out[3];  // device staging for the batch_host pipeline
+    cb::Workspace ws_band_parent;         // union-find slots of the resident band (row-band sharding)
+    cb::Workspace ws_band_aux;            // boundary roots of the resident band + the cross-band forest
+    int chunk_frames = 0;
+    long long launches = 0;
+    cb::Profiler prof;
+    // band state (row-band sharding)
+    int band_rows = 0, band_width = 0, band_row0 = 0;
+    uint8_t* band_cls = nullptr;          // class map of the resident band (caller's d_edges)
+};
+
+namespace cb {
+
+struct ProfScope {  // RAII: records an event before and after whatever is launched inside its lifetime
+    b200_ctx* ctx; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr; int cat;
+    ProfScope(b200_ctx* c, cudaStream_t s, int category) : ctx(c), st(s), cat(category) {
+        if (!ctx->prof.on) return;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, st);
+    }
+    ~ProfScope() {
+        if (!a) return;
+        cudaEventRecord(b, st);
+        ctx->prof.recs.push_back({cat, a, b});
+    }
+};
+
+int ensure_ws(Workspace& ws, size_t bytes, bool pinned_host = false);
+int prepare_gauss(b200_ctx* ctx, float sigma);
+void host_gaussian_kernel(float sigma, std::vector<float>& w);
+int host_window(float sigma);
+
+// front.cu
+int launch_front(b200_ctx* ctx, cudaStream_t st, const FrontParams& p);
+// hysteresis.cu
+int launch_hysteresis(b200_ctx* ctx, cudaStream_t st, const HystParams& p);   // label + resolve
+int launch_ccl_label(b200_ctx* ctx, cudaStream_t st, const HystParams& p);    // tile-local forest + tile-boundary unions
+int launch_ccl_resolve(b200_ctx* ctx, cudaStream_t st, const HystParams& p);  // weak pixels -> 0/255 in place
+int launch_classify_i16(b200_ctx* ctx, cudaStream_t st, const int16_t* nms, uint8_t* cls, size_t n,
+                        int lo, int hi);
+int launch_expand_u8_to_i16(b200_ctx* ctx, cudaStream_t st, const uint8_t* cls, int16_t* out, size_t n);
+// stages.cu
+int launch_xy_gradient(b200_ctx* ctx, cudaStream_t st, const int16_t* blur, int h, int w, int16_t* gx,
+                       int16_t* gy);
+int launch_sobel(b200_ctx* ctx, cudaStream_t st, const int16_t* blur, int h, int w, int16_t* mag,
+                 int16_t* ang);
+int launch_nonmaximal(b200_ctx* ctx, cudaStream_t st, const int16_t* mag, const int16_t* ang, int h,
+                      int w, int16_t* out);
+// synth.cu
+int launch_synth(b200_ctx* ctx, cudaStream_t st, uint8_t* d, int n_frames, int row0, int rows, int width,
+                 int kind, uint64_t seed, int first_frame);
+int launch_count255(b200_ctx* ctx, cudaStream_t st, const uint8_t* d, size_t n, unsigned long long* d_count);
+
+}  // namespace cb

@@ -1,0 +1,98 @@
+// selftest.cu — device-side table dumps used by the GPU tests to check the exact-arithmetic
+// building blocks of front.cu over their WHOLE domain (not just on images).
+#include "canny_math.h"
+#include "exact_math.cuh"
+#include "internal.h"
+
+namespace cb {
+
+__global__ void direction_table_kernel(int gmax, int16_t* __restrict__ out) {
+    const int n = 2 * gmax + 1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)n * n; i += (long long)gridDim.x * blockDim.x) {
+        const int gy = (int)(i / n) - gmax, gx = (int)(i % n) - gmax;
+        out[i] = (int16_t)dir_code_to_angle(direction_code<int>(gx, gy));
+    }
+}
+__global__ void isqrt_table_kernel(int n_max, int32_t* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i <= n_max; i += (long long)gridDim.x * blockDim.x)
+        out[i] = isqrt_floor((int)i);
+}
+// every float a in [0, 256*b] (bit patterns 0 .. bits(256*b)) for every entry b of the count table
+__global__ void div_check_kernel(const float* __restrict__ cnt, const float* __restrict__ rcp, int n_tab,
+                                 unsigned long long* __restrict__ mismatches) {
+    const int t = blockIdx.y;
+    if (t >= n_tab) return;
+    const float b = cnt[t], y = rcp[t];
+    if (!(b > 0.f)) return;
+    const unsigned last = __float_as_uint(256.0f * b);
+    unsigned long long bad = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i <= last;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const float a = __uint_as_float((unsigned)i);
+        const float q = div_exact(a, b, y), ref = __fdiv_rn(a, b);
+        if (__float_as_uint(q) != __float_as_uint(ref)) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+extern "C" {
+
+int b200_direction_table_host(int gmax, int16_t* out) {
+    if (!out || gmax < 0 || gmax > 20000) { set_error("bad argument"); return B200_ERR_INVALID_ARG; }
+    const int n = 2 * gmax + 1;
+    for (int gy = -gmax; gy <= gmax; ++gy)
+        for (int gx = -gmax; gx <= gmax; ++gx)
+            out[(size_t)(gy + gmax) * n + (gx + gmax)] = (int16_t)dir_code_to_angle(direction_code<long long>(gx, gy));
+    return B200_OK;
+}
+
+int b200_direction_table_device(b200_ctx* ctx, int gmax, int16_t* out_host) {
+    if (!ctx || !out_host || gmax < 0 || gmax > 1020) { set_error("bad argument"); return B200_ERR_INVALID_ARG; }
+    CB_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)(2 * gmax + 1) * (2 * gmax + 1);
+    CB_TRY(ensure_ws(ctx->ws_planes, n * 2));
+    int16_t* d = reinterpret_cast<int16_t*>(ctx->ws_planes.ptr);
+    direction_table_kernel<<<1024, 256, 0, ctx->stream>>>(gmax, d);
+    CB_CUDA(cudaGetLastError());
+    ctx->launches++;
+    CB_CUDA(cudaMemcpyAsync(out_host, d, n * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+
+int b200_isqrt_table_device(b200_ctx* ctx, int n_max, int32_t* out_host) {
+    if (!ctx || !out_host || n_max < 0 || n_max > (1 << 24)) { set_error("bad argument"); return B200_ERR_INVALID_ARG; }
+    CB_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)n_max + 1;
+    CB_TRY(ensure_ws(ctx->ws_planes, n * 4));
+    int32_t* d = reinterpret_cast<int32_t*>(ctx->ws_planes.ptr);
+    isqrt_table_kernel<<<1024, 256, 0, ctx->stream>>>(n_max, d);
+    CB_CUDA(cudaGetLastError());
+    ctx->launches++;
+    CB_CUDA(cudaMemcpyAsync(out_host, d, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+
+int b200_division_check_device(b200_ctx* ctx, float sigma, unsigned long long* mismatches) {
+    if (!ctx || !mismatches) { set_error("bad argument"); return B200_ERR_INVALID_ARG; }
+    CB_CUDA(cudaSetDevice(ctx->device));
+    CB_TRY(prepare_gauss(ctx, sigma));
+    const int n1 = ctx->gauss.radius + 1, n_tab = n1 * n1;
+    CB_TRY(ensure_ws(ctx->ws_misc, 256));
+    unsigned long long* d = reinterpret_cast<unsigned long long*>(ctx->ws_misc.ptr);
+    CB_CUDA(cudaMemsetAsync(d, 0, sizeof(*d), ctx->stream));
+    dim3 grid(592, n_tab);
+    div_check_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->gauss.d_count, ctx->gauss.d_count + n_tab, n_tab, d);
+    CB_CUDA(cudaGetLastError());
+    ctx->launches++;
+    CB_CUDA(cudaMemcpyAsync(mismatches, d, sizeof(*d), cudaMemcpyDeviceToHost, ctx->stream));
+    CB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,232 @@
+/*
+ * canny_b200.h — C ABI of the B200-native Canny hot path (libcanny_b200.so).
+ *
+ * This is the drop-in boundary for StevenChang5/Canny_Edge's GPU stage API.  Every entry point names
+ * the reference interface it replaces (paths relative to the reference checkout).  Plain pointers and
+ * sizes only; no C++ or torch types.  All images are row-major, contiguous (pitch == width) exactly
+ * as the reference's Mat.data convention (src/utils.cpp:12-15).
+ *
+ * There is NO CPU fallback: every compute entry point runs hand-written sm_100a kernels and returns
+ * B200_ERR_NO_DEVICE / B200_ERR_CUDA when that is impossible.
+ *
+ * Error convention.  The reference returns void and checks no CUDA status (src/cuda.cu:83-101).  The
+ * C ABI returns an int status (0 == B200_OK) and keeps a thread-local message readable through
+ * b200_last_error().  Argument domains follow the reference: height,width >= 2 (below that the
+ * reference's gradient reads out of bounds, src/utils.cpp:117,158), sigma > 0; thresholds are accepted
+ * over the whole int range and behave as src/utils.cpp:322-342 does (the CLI's 0 <= lo < hi <= 255
+ * check lives in src/main.cpp:63-76 and stays there).
+ */
+#ifndef CANNY_B200_H
+#define CANNY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_ERR_INVALID_ARG 1 /* bad pointer / size / sigma                                    */
+#define B200_ERR_NO_DEVICE 2   /* no CUDA device, or the device is not sm_100                    */
+#define B200_ERR_CUDA 3        /* a CUDA runtime / driver call failed (see b200_last_error)     */
+#define B200_ERR_UNSUPPORTED 4 /* valid in the reference but outside this build's limits         */
+#define B200_ERR_NOMEM 5
+
+/* Constants of src/utils.h:5-6. */
+#define B200_EDGE 255
+#define B200_NOEDGE 0
+
+/* Largest Gaussian half-window (window/2) the kernels are built for: sigma <= 16. */
+#define B200_MAX_RADIUS 48
+
+typedef struct b200_ctx b200_ctx; /* opaque: device, streams, workspace pool, cached tables */
+
+/* ------------------------------------------------------------------ library / context ---------- */
+
+int b200_version(void);              /* ABI version, bumped on any signature change             */
+const char* b200_last_error(void);   /* thread-local text of the last non-OK status             */
+
+/* Creates a context on CUDA device `device` (>= 0).  Replaces the reference's per-call
+ * cudaMalloc/cudaFree (src/cuda.cu:83-86,98-101 and the same pattern in every wrapper) with a
+ * persistent workspace pool, streams and pinned staging. */
+int b200_ctx_create(int device, b200_ctx** out);
+int b200_ctx_destroy(b200_ctx* ctx);
+/* Makes the context issue work on an existing cudaStream_t (e.g. torch's current stream) instead of
+ * its own; pass NULL to go back to the context's private stream. */
+int b200_ctx_set_stream(b200_ctx* ctx, void* cuda_stream);
+/* Blocks until everything issued on the context has finished. */
+int b200_ctx_synchronize(b200_ctx* ctx);
+/* Frames per internal chunk for batch calls (0 = automatic: sized so a chunk's intermediates stay in
+ * the 126 MB L2). */
+int b200_ctx_set_chunk_frames(b200_ctx* ctx, int frames);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+long long b200_ctx_kernel_launches(const b200_ctx* ctx);
+
+/* In every function below ctx may be NULL: a lazily created process-wide context on the current
+ * CUDA device is used (what the reference-signature C++ shims in canny_b200_compat.hpp do). */
+
+/* ------------------------------------------------------------------ host-side helpers ----------- */
+
+/* window = 1 + 2*ceil(3*sigma)                         — src/utils.cpp:78, src/cuda.cu:78 */
+int b200_gaussian_window(float sigma);
+/* createGaussianKernel(float*&, float, int*)            — src/utils.cpp:77-95 and the host overload
+ * src/cuda.cu:15-30.  Host code (as in the reference); w must hold b200_gaussian_window(sigma)
+ * floats. */
+int b200_gaussian_kernel(float sigma, float* w, int* window);
+/* Exact integer form of the reference's atan2 binning (src/utils.cpp:215-231) as the kernels use
+ * it, evaluated on the HOST for table tests: returns 0, 45, 90 or 135. Valid for |gx|,|gy| <= 1020. */
+int b200_direction_host(int gx, int gy);
+/* floor(sqrt(n)) as the kernels compute magnitude (src/utils.cpp:212), host evaluation. */
+int b200_isqrt_host(int n);
+
+/* ------------------------------------------------------------------ stage API, host buffers ---- */
+
+/* cuda_gaussian(unsigned char*& img_h, float sigma, int height, int width, short*& result_h)
+ *                                                       — src/cuda.h:4, src/cuda.cu:75-102
+ * (CPU twin gaussian(), src/utils.cpp:26-68).  blur: caller-allocated height*width int16. */
+int b200_gaussian(b200_ctx* ctx, const uint8_t* img, float sigma, int height, int width,
+                  int16_t* blur);
+
+/* calculateXYGradient(short*& img, int h, int w, short*& grad_x, short*& grad_y)
+ *                                                       — src/utils.h:12, src/utils.cpp:106-187
+ * (the reference GPU path fuses this into sobel_util, src/cuda.cu:185-191, with a flipped gy sign;
+ * this follows the CPU semantics). */
+int b200_xy_gradient(b200_ctx* ctx, const int16_t* blur, int height, int width, int16_t* grad_x,
+                     int16_t* grad_y);
+
+/* cuda_sobel(short*& img_h, int height, int width, short*& magnitude_h, short*& angle_h)
+ *                                                       — src/cuda.h:6, src/cuda.cu:220-246
+ * (CPU twin sobelOperator(), src/utils.cpp:201-236; unlike it the input is NOT freed, matching
+ * cuda_sobel).  angle holds 0/45/90/135. */
+int b200_sobel(b200_ctx* ctx, const int16_t* blur, int height, int width, int16_t* magnitude,
+               int16_t* angle);
+
+/* cuda_nonmaixmal_suppression(short*& magnitude_h, short*& angle_h, int height, int width,
+ *                             short*& result_h)         — src/cuda.h:8, src/cuda.cu:366-390
+ * (CPU twin nonmaximalSuppression(), src/utils.cpp:248-308; inputs are NOT freed). */
+int b200_nonmaximal(b200_ctx* ctx, const int16_t* magnitude, const int16_t* angle, int height,
+                    int width, int16_t* nms);
+
+/* hysteresis(short*& edgeCandidates, int height, int width, int minVal, int maxVal)
+ *                                                       — src/utils.h:18, src/utils.cpp:322-342
+ * + findEdgePixels (src/utils.cpp:360-427).  The reference has no GPU hysteresis (cuda_canny calls
+ * the CPU one, src/cuda.cu:436); this runs it as GPU connected components.  In place: on return every
+ * element is 0 or 255. */
+int b200_hysteresis(b200_ctx* ctx, int16_t* nms_inout, int height, int width, int min_val,
+                    int max_val);
+
+/* cuda_canny(unsigned char* img, float sigma, int min_val, int max_val, int height, int width,
+ *            bool steps)                                — src/cuda.h:10, src/cuda.cu:392-450
+ * (CPU twin canny(), src/utils.cpp:429-492).  The reference only displays its result; here the 0/255
+ * map is returned in `edges` (int16, the type of the array the reference shows, src/cuda.cu:439).
+ * Fused path: one H2D, two kernel phases, one D2H. */
+int b200_canny(b200_ctx* ctx, const uint8_t* img, float sigma, int min_val, int max_val, int height,
+               int width, int16_t* edges);
+
+/* The `steps` flag of cuda_canny (src/cuda.cu:400-434): additionally returns the planes the
+ * reference would display after each stage.  Any of blur/magnitude/angle/nms may be NULL. */
+int b200_canny_steps(b200_ctx* ctx, const uint8_t* img, float sigma, int min_val, int max_val,
+                     int height, int width, int16_t* blur, int16_t* magnitude, int16_t* angle,
+                     int16_t* nms, int16_t* edges);
+
+/* ------------------------------------------------------------------ batched, u8 edge maps ------ */
+
+/* n_frames independent frames, host memory in, host memory out (u8, 0/255).  What main.cpp's frame
+ * loop (src/main.cpp:120-137) becomes for N frames: chunked, H2D / kernels / D2H overlapped on
+ * separate streams through pinned staging.  frames: n_frames*height*width bytes. */
+int b200_canny_batch_host(b200_ctx* ctx, const uint8_t* frames, int n_frames, int height, int width,
+                          float sigma, int min_val, int max_val, uint8_t* edges);
+
+/* Same with DEVICE pointers (already resident in HBM): d_frames and d_edges are n_frames*height*width
+ * bytes each, on the context's device.  Asynchronous on the context's stream.  d_edges may not alias
+ * d_frames. */
+int b200_canny_batch_device(b200_ctx* ctx, const uint8_t* d_frames, int n_frames, int height,
+                            int width, float sigma, int min_val, int max_val, uint8_t* d_edges);
+
+/* The same work as b200_canny_batch_device, issued serially on the context's stream with a CUDA event
+ * pair around every kernel; blocks, then returns per-kernel-class totals: ms_out[5] / launches_out[5]
+ * indexed 0 = front (blur+Sobel+NMS+classify), 1 = ccl_local, 2 = ccl_merge, 3 = ccl_final, 4 = other.
+ * This is how bench.py measures the dominant kernel's launch duration for its roofline entry. */
+int b200_profile_stages_device(b200_ctx* ctx, const uint8_t* d_frames, int n_frames, int height,
+                               int width, float sigma, int min_val, int max_val, uint8_t* d_edges,
+                               float* ms_out, int* launches_out);
+
+/* ------------------------------------------------------------------ row-band sharding ---------- */
+
+/* One image of global_height rows split into row bands, one band per GPU/rank (BASELINE config 5).
+ * A band owns global rows [row0, row0+band_rows).  Stages 1-3 need b200_band_halo_rows(sigma) input
+ * rows beyond each interior band edge (window/2 for the blur + 1 Sobel + 1 NMS).
+ *
+ * b200_band_front : d_rows points at global row (row0 - halo_above); halo_above/halo_below say how
+ *   many real rows are present above/below the band (0 at the image's true top/bottom, otherwise
+ *   b200_band_halo_rows).  Runs stages 1-3 + classification and the band-local connected components.
+ *   Afterwards d_edges (band_rows*width) holds 0 / 1 (weak) / 255 (strong) and the band's label state
+ *   is kept in the context.
+ * b200_band_boundary_export : writes this band's first and last row as (label, flags) records into
+ *   d_records[b200_band_record_count(width)], ready to be all-gathered (NCCL) by the caller.
+ * b200_band_finalize : given ALL bands' records (n_bands*b200_band_record_count(width), band order), merges label
+ *   equivalences across every band boundary (8-connectivity across the boundary, including the
+ *   reference's missing (1,0)->(0,1) link when that pair straddles nothing — it never does for
+ *   band_rows >= 2), decides which local components become strong and rewrites d_edges to 0/255.
+ */
+typedef struct b200_band_record {
+    int32_t label; /* canonical record index of the pixel's band-local component (same label == same
+                      component inside that band); -1 when not a candidate or already strong          */
+    int32_t flags; /* bit1 = pixel is a candidate (>= minVal); bit0 = its component contains a seed   */
+} b200_band_record;
+
+/* records a band exports: its first row (width), its last row (width), and the two pixels (0,1), (1,0)
+ * of the reference's missing link (src/utils.cpp:399), present only in the band that owns row 0. */
+int b200_band_record_count(int width);
+int b200_band_halo_rows(float sigma);
+int b200_band_front(b200_ctx* ctx, const uint8_t* d_rows, int halo_above, int halo_below,
+                    int band_rows, int row0, int global_height, int width, float sigma, int min_val,
+                    int max_val, uint8_t* d_edges);
+int b200_band_boundary_export(b200_ctx* ctx, int band_rows, int width, b200_band_record* d_records);
+int b200_band_finalize(b200_ctx* ctx, const b200_band_record* d_all_records, int n_bands,
+                       int band_index, int band_rows, int width, uint8_t* d_edges);
+
+/* ------------------------------------------------------------------ synthetic workloads -------- */
+
+/* Procedural test frames (pure integer hash; identical bytes on host and device) used by bench.py
+ * and the parity tests.  kind: 0 = "shapes" (smooth background + discs + mild noise),
+ * 1 = uniform noise (hysteresis worst case), 2 = constant 128.  Frame f of a batch uses
+ * frame index first_frame + f. */
+int b200_synth_host(uint8_t* frames, int n_frames, int height, int width, int kind, uint64_t seed,
+                    int first_frame);
+int b200_synth_device(b200_ctx* ctx, uint8_t* d_frames, int n_frames, int height, int width,
+                      int kind, uint64_t seed, int first_frame);
+/* Same generator for a row range [row0, row0+rows) of one frame of global_height rows (band tests). */
+int b200_synth_rows_host(uint8_t* rows_out, int row0, int rows, int width, int kind, uint64_t seed,
+                         int frame);
+int b200_synth_rows_device(b200_ctx* ctx, uint8_t* d_rows, int row0, int rows, int width, int kind,
+                           uint64_t seed, int frame);
+
+/* ------------------------------------------------------------------ self-tests ----------------- */
+/* Whole-domain dumps of the exact-arithmetic building blocks (tests/): the angle (0/45/90/135) for
+ * every (gx,gy) in [-gmax,gmax]^2, row-major by gy then gx, from the host classifier and from the
+ * device one; floor(sqrt(n)) for n = 0..n_max as the kernels compute it; and an exhaustive comparison
+ * of the kernels' Markstein division against IEEE division for every numerator in [0, 256*count] and
+ * every entry of sigma's count table (mismatch count returned). */
+int b200_direction_table_host(int gmax, int16_t* out);
+int b200_direction_table_device(b200_ctx* ctx, int gmax, int16_t* out_host);
+int b200_isqrt_table_device(b200_ctx* ctx, int n_max, int32_t* out_host);
+int b200_division_check_device(b200_ctx* ctx, float sigma, unsigned long long* mismatches);
+
+/* Device-side count of 255 bytes in a u8 buffer (edge pixels), written to *count. */
+int b200_count_edges_device(b200_ctx* ctx, const uint8_t* d_edges, size_t n, unsigned long long* count);
+
+/* Raw device memory helpers so non-CUDA hosts (ctypes, cgo, JNI) can stage data without a CUDA
+ * binding of their own. */
+int b200_device_alloc(b200_ctx* ctx, size_t bytes, void** d_ptr);
+int b200_device_free(b200_ctx* ctx, void* d_ptr);
+int b200_memcpy_h2d(b200_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
+int b200_memcpy_d2h(b200_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+int b200_host_alloc_pinned(size_t bytes, void** h_ptr);
+int b200_host_free_pinned(void* h_ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CANNY_B200_H */

@@ -99,6 +99,11 @@ int prepare_gauss(b200_ctx* ctx, float sigma) {
     CB_CUDA(cudaMemcpyAsync(g.d_w, g.w.data(), sizeof(float) * g.w.size(), cudaMemcpyHostToDevice, ctx->stream));
     CB_CUDA(cudaMemcpyAsync(g.d_count, g.count.data(), sizeof(float) * g.count.size(), cudaMemcpyHostToDevice, ctx->stream));
     CB_CUDA(cudaStreamSynchronize(ctx->stream));
+    {
+        float wmin = g.w[0];
+        for (float v : g.w) wmin = v < wmin ? v : wmin;
+        g.tiny = !((double)wmin * (double)wmin >= 8.077935669463161e-28);  // 2^-90
+    }
     g.sigma = sigma;
     g.window = window;
     g.radius = radius;

@@ -40,9 +40,12 @@ constexpr int kNdPitch = 132;    // int32; column j <-> image x = x0 - 4 + j (cl
 constexpr int kRunS = 16;        // outputs per blur_run
 
 __host__ __device__ constexpr int in_pitch_for(int radius) {
-    // bytes per staged input row: >= kTC + 2*radius, a multiple of 16 (TMA box rule) and an ODD
-    // multiple of 16 so that lane = row 128-bit shared loads hit 8 distinct bank groups.
-    int k = (kTC + 2 * radius + 15) / 16;
+    // Bytes per staged input row.  TMA needs the box's first column to sit on a 16-byte boundary of the image
+    // row (measured: an unaligned innermost coordinate raises an illegal-instruction fault), so the box starts
+    // at the aligned column at or before x0-2-radius and carries up to 15 extra leading bytes.  The pitch is
+    // a multiple of 16 (TMA box rule) and an ODD multiple, so that lane = row 128-bit shared loads spread over
+    // 8 distinct bank groups.
+    int k = (15 + kTC + 2 * radius + 15) / 16;
     if ((k & 1) == 0) k += 1;
     return 16 * k;
 }
@@ -178,7 +181,8 @@ front_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
     const int W = p.width, H = p.height;
     const int n_slabs = (ye - yb + 2 * radius + 4 + kSlab - 1) / kSlab;
     const int in_y0 = yb - 2 - radius;               // global row of slab 0, line 0
-    const int in_x0 = x0 - 2 - radius;               // global column of staged byte 0
+    const int lead = (x0 - 2 - radius) & 15;         // bytes between the 16 B aligned box origin and the first needed column
+    const int in_x0 = x0 - 2 - radius - lead;        // global column of staged byte 0 (a multiple of 16, may be negative)
     // ring rows are addressed by (global row + kBias) & mask; kBias keeps the operand positive
     constexpr int kBias = 1 << 20;
 
@@ -202,6 +206,8 @@ front_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
 #pragma unroll
         for (int j = 0; j <= R; ++j) ws[j] = s_w[R + j];
     }
+    const bool ieee = p.ieee_div != 0;  // uniform; only for sigma < ~0.15 (see exact_math.cuh)
+    auto divq = [&](float a, float b, float y) { return ieee ? __fdiv_rn(a, b) : div_exact(a, b, y); };
     const float cnt_full = s_cnt[0], rcp_full = s_rcp[0];
     // strips whose every computed column has all its taps inside the image use the constant count
     const bool x_interior = (x0 - 2 - radius >= 0) && (x0 - 2 + kTC - 1 + radius <= W - 1);
@@ -255,25 +261,49 @@ front_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
             const int gx_first = x0 - 2 + warp * kRunS;  // image column of output 0
             float outv[kRunS];
             if (R) {
-                // staged bytes [16*warp, 16*warp + 16 + 2R) of this line: ceil((16+2R)/16) aligned 128-bit loads
-                constexpr int NW = (kRunS + 2 * (R ? R : 1) + 15) / 16;
-                uint32_t wv[NW * 4];
+                // needed bytes of this line: [16*warp + lead, 16*warp + lead + 16 + 2R).  lead = 4*dq + DR where DR is
+                // a compile-time constant (x0 is a multiple of 4) and dq in 0..3 is uniform over the CTA: load whole
+                // aligned 128-bit vectors, shift by dq WORDS with a uniform switch, pick bytes with static selectors.
+                constexpr int RR = R ? R : 1;
+                constexpr int DR = (((-2 - RR) % 4) + 4) % 4;
+                constexpr int KW = (DR + kRunS + 2 * RR + 3) / 4;       // words holding the needed bytes
+                constexpr int NV = (KW + 3 + 3) / 4;                    // vectors covering KW + 3 words
+                uint32_t wv[NV * 4];
                 const uint4* src = reinterpret_cast<const uint4*>(slab + lane * in_pitch + warp * kRunS);
 #pragma unroll
-                for (int v = 0; v < NW; ++v) {
+                for (int v = 0; v < NV; ++v) {
                     uint4 t4 = src[v];
                     wv[4 * v + 0] = t4.x; wv[4 * v + 1] = t4.y; wv[4 * v + 2] = t4.z; wv[4 * v + 3] = t4.w;
                 }
-                blur_run<(R ? R : 1), kRunS>(
+                uint32_t w2[KW];
+                switch (lead >> 2) {
+                    case 0:
+#pragma unroll
+                        for (int q = 0; q < KW; ++q) w2[q] = wv[q];
+                        break;
+                    case 1:
+#pragma unroll
+                        for (int q = 0; q < KW; ++q) w2[q] = wv[q + 1];
+                        break;
+                    case 2:
+#pragma unroll
+                        for (int q = 0; q < KW; ++q) w2[q] = wv[q + 2];
+                        break;
+                    default:
+#pragma unroll
+                        for (int q = 0; q < KW; ++q) w2[q] = wv[q + 3];
+                        break;
+                }
+                blur_run<RR, kRunS>(
                     ws,
                     [&](int i) {
-                        const uint32_t word = wv[i >> 2];
-                        const uint32_t bits = __byte_perm(word, 0x4B000000u, 0x7650 + (i & 3));
+                        const uint32_t word = w2[(i + DR) >> 2];
+                        const uint32_t bits = __byte_perm(word, 0x4B000000u, 0x7650 + ((i + DR) & 3));
                         return __fsub_rn(__uint_as_float(bits), 8388608.0f);
                     },
                     [&](int o, float s) { outv[o] = s; });
             } else {
-                const unsigned char* src = slab + lane * in_pitch + warp * kRunS;
+                const unsigned char* src = slab + lane * in_pitch + warp * kRunS + lead;
                 for (int o = 0; o < kRunS; ++o) {
                     float s = 0.f;
                     for (int t = 0; t <= 2 * radius; ++t) s = __fadd_rn(s, __fmul_rn((float)src[o + t], s_w[t]));
@@ -283,7 +313,7 @@ front_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
             // divide by the in-image weight sum (src/utils.cpp:47)
             if (x_interior) {
 #pragma unroll
-                for (int o = 0; o < kRunS; ++o) outv[o] = div_exact(outv[o], cnt_full, rcp_full);
+                for (int o = 0; o < kRunS; ++o) outv[o] = divq(outv[o], cnt_full, rcp_full);
             } else {
 #pragma unroll
                 for (int o = 0; o < kRunS; ++o) {
@@ -291,7 +321,7 @@ front_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
                     if (gx < 0 || gx >= W) { outv[o] = 0.f; continue; }
                     const int a = max(0, radius - gx), b = max(0, gx + radius - (W - 1));
                     const int ti = a * (radius + 1) + b;
-                    outv[o] = div_exact(outv[o], s_cnt[ti], s_rcp[ti]);
+                    outv[o] = divq(outv[o], s_cnt[ti], s_rcp[ti]);
                 }
             }
 #pragma unroll
@@ -329,13 +359,13 @@ front_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
                 const int gy = b0 + o;
                 float q;
                 if (y_interior) {
-                    q = div_exact(outv[o], cnt_full, rcp_full);
+                    q = divq(outv[o], cnt_full, rcp_full);
                 } else if (gy < 0 || gy >= H) {
                     q = 0.f;
                 } else {
                     const int a = max(0, radius - gy), b = max(0, gy + radius - (H - 1));
                     const int ti = a * (radius + 1) + b;
-                    q = div_exact(outv[o], s_cnt[ti], s_rcp[ti]);
+                    q = divq(outv[o], s_cnt[ti], s_rcp[ti]);
                 }
                 const int bi = (int)q;  // (short)(sum/count): C truncation, values are >= 0
                 s_blur[((gy + kBias) & (kRingCap - 1)) * kBlurPitch + c] = (int16_t)bi;
@@ -540,6 +570,7 @@ int choose_bands(const b200_ctx* ctx, int out_rows, int strips, int frames, int 
 
 int launch_front(b200_ctx* ctx, cudaStream_t st, const FrontParams& p_in) {
     FrontParams p = p_in;
+    p.ieee_div = ctx->gauss.tiny ? 1 : 0;
     const int radius = p.radius;
     if (radius < 1 || radius > B200_MAX_RADIUS) {
         set_error("gaussian radius %d outside [1,%d]", radius, B200_MAX_RADIUS);

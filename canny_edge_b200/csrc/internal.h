@@ -37,6 +37,7 @@ struct GaussTables {
                                // exactly as src/utils.cpp:44,59 do
     float* d_w = nullptr;      // device copies (owned by the context)
     float* d_count = nullptr;
+    bool tiny = false;         // min weight^2 < 2^-90: blur sums may approach the subnormal range
 };
 
 // ---- parameters of the fused front kernel -----------------------------------------------------
@@ -63,6 +64,7 @@ struct FrontParams {
     int lo2, hi2;           // thresholds in squared-magnitude space (see front.cu)
     int lo, hi;             // raw thresholds (spill / zero-class decisions)
     int cls_zero;           // class of a suppressed pixel (value 0): nonzero only when lo <= 0
+    int ieee_div;           // 1: weights so small that sums can fall below 2^-100 -> use IEEE division instead of div_exact
     int tiles_x, tiles_y;
 };
 

@@ -17,21 +17,25 @@ __global__ void isqrt_table_kernel(int n_max, int32_t* __restrict__ out) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i <= n_max; i += (long long)gridDim.x * blockDim.x)
         out[i] = isqrt_floor((int)i);
 }
-// every float a in [0, 256*b] (bit patterns 0 .. bits(256*b)) for every entry b of the count table
+// every float a in {0} u [2^-100, 256*b] for every entry b of the count table.  (Below 2^-100 the quotient
+// nears the subnormal range where the residuals stop being exact; the front kernel switches to IEEE division
+// when sigma is so small that such sums can occur — see FrontParams::ieee_div.)
 __global__ void div_check_kernel(const float* __restrict__ cnt, const float* __restrict__ rcp, int n_tab,
                                  unsigned long long* __restrict__ mismatches) {
     const int t = blockIdx.y;
     if (t >= n_tab) return;
     const float b = cnt[t], y = rcp[t];
     if (!(b > 0.f)) return;
+    const unsigned first = __float_as_uint(7.888609052210118e-31f);  // 2^-100
     const unsigned last = __float_as_uint(256.0f * b);
     unsigned long long bad = 0;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i <= last;
+    for (unsigned long long i = first + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i <= last;
          i += (unsigned long long)gridDim.x * blockDim.x) {
         const float a = __uint_as_float((unsigned)i);
         const float q = div_exact(a, b, y), ref = __fdiv_rn(a, b);
         if (__float_as_uint(q) != __float_as_uint(ref)) ++bad;
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && __float_as_uint(div_exact(0.f, b, y)) != 0u) ++bad;
     if (bad) atomicAdd(mismatches, bad);
 }
 

@@ -236,11 +236,14 @@ def test_device_batch_and_synth_match_host(gpu_ctx, oracle):
     d_in = torch.empty((n, h, w), dtype=torch.uint8, device="cuda")
     d_out = torch.empty_like(d_in)
     lib = load()
-    gpu_ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    gpu_ctx.set_stream(stream.cuda_stream)
     check(lib.b200_synth_device(gpu_ctx.handle, d_in.data_ptr(), n, h, w, 0, 1234, 7))
     cb.canny_batch_device_ptr(gpu_ctx, d_in.data_ptr(), n, h, w, 1.4, 20, 60, d_out.data_ptr())
     torch.cuda.synchronize()
     gpu_ctx.set_stream(0)
+    torch.cuda.set_stream(torch.cuda.default_stream())
     host = cb.synth_host(n, h, w, kind=0, seed=1234, first_frame=7)
     assert_same("synth", d_in.cpu().numpy(), host)
     got = d_out.cpu().numpy()

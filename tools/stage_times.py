@@ -29,7 +29,9 @@ a = ap.parse_args()
 
 lib = load()
 ctx = cb.Context(0)
-ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+stream = torch.cuda.Stream()  # a real (non-default) stream: events below are recorded on the stream the kernels run on
+torch.cuda.set_stream(stream)
+ctx.set_stream(stream.cuda_stream)
 ctx.set_chunk_frames(a.chunk)
 n, h, w = a.frames, a.height, a.width
 d_in = torch.empty((n, h, w), dtype=torch.uint8, device="cuda")

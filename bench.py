@@ -48,6 +48,12 @@ def parse():
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the CPU sample (0 = one per core, <= 32)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="frames", choices=["frames", "bands"],
+                    help="frames: batch of frames per GPU (BASELINE configs[2], the default); bands: ONE image of --band-height x "
+                         "--band-width split into row bands across the GPUs (configs[4]; strong scaling, NCCL halo + label exchange)")
+    ap.add_argument("--band-height", type=int, default=32768)
+    ap.add_argument("--band-width", type=int, default=32768)
+    ap.add_argument("--sigma", type=float, default=SIGMA)
     return ap.parse_args()
 
 
@@ -316,6 +322,86 @@ def run_b200(a, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_bands(a, rank, world, local_rank):
+    """configs[4]: one --band-height x --band-width image, row-band sharded; every step = halo exchange (NCCL send/recv) +
+    band front kernel + band-local labelling + record all-gather + cross-band union + finalisation."""
+    import torch
+    import torch.distributed as dist
+
+    import canny_edge_b200 as cb
+    from canny_edge_b200 import sharded
+    from canny_edge_b200._lib import check, load
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = load()
+    ctx = cb.Context(local_rank)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    H, W = a.band_height, a.band_width
+    pipe = sharded.BandPipeline(ctx, H, W, rank, world, a.sigma, LO, HI)
+    g = pipe.geo
+    band = torch.empty((g.rows, W), dtype=torch.uint8, device="cuda")
+    edges = torch.empty_like(band)
+    check(lib.b200_synth_rows_device(ctx.handle, band.data_ptr(), g.row0, g.rows, W, a.kind, 1234, 0))
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        pipe.run(band, edges)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctx.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        pipe.run(band, edges)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.kernel_launches - l0
+    ms = e0.elapsed_time(e1)
+    cnt = C.c_ulonglong()
+    check(lib.b200_count_edges_device(ctx.handle, edges.data_ptr(), edges.numel(), C.byref(cnt)))
+    tot = torch.tensor([float(cnt.value)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.all_reduce(tot)
+    px = H * W
+    value = px * a.steps / (ms * 1e-3) / 1e6
+    peak, peak_src = peaks()
+    halo_bytes = 2 * g.halo * W if world > 1 else 0
+    if rank == 0:
+        print(json.dumps({
+            "metric": "end-to-end Canny Mpix/s (row-band sharded image)", "value": round(value, 1), "unit": "Mpix/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms / a.steps, 4), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32 blur (reference roundings) + int16/int32 gradient/NMS + u8 labels", "data": "synthetic",
+            "config": {"workload": f"single {W}x{H} synthetic image, sigma={a.sigma}, thresholds {LO}/{HI}, row-band sharded over {world} GPU(s) "
+                                   "(BASELINE configs[4])", "height": H, "width": W, "sigma": a.sigma, "bands": world,
+                       "band_rows": g.rows, "halo_rows": g.halo, "halo_bytes_per_interior_rank_per_step": halo_bytes,
+                       "record_bytes_all_gathered_per_step": world * pipe.n_records * 8,
+                       "generator": ["shapes", "noise", "const"][a.kind],
+                       "l2": "band (%.2f GB per GPU) exceeds the 126 MB L2" % (g.rows * W / 1e9)},
+            "clocks": clocks, "gpu_launches": int(launches), "edge_fraction": round(float(tot.item()) / px, 6),
+            "roofline": {"bound": "hbm", "kernel": "whole band pipeline", "achieved": round(value * 1e6 * ALG_BYTES_PER_PX / 1e9 / world, 2),
+                         "peak": peak, "unit": "GB/s", "frac": round(value * 1e6 * ALG_BYTES_PER_PX / 1e9 / world / peak, 5),
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_px": ALG_BYTES_PER_PX},
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -323,6 +409,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if a.impl == "reference":
         run_reference(a, rank, world)
+        return
+    if a.workload == "bands":
+        run_bands(a, rank, world, local_rank)
         return
     run_b200(a, rank, world, local_rank)
 

@@ -1,0 +1,195 @@
+"""Sharding of the Canny hot path across GPUs: one process per GPU, torch.distributed as plumbing.
+
+Two ways the path shards (the reference itself is single-GPU, single-frame, src/main.cpp:111):
+
+* frames   — independent units; rank r owns frames [r*n, (r+1)*n).  No data-path collective.
+             (`frame_slice`; bench.py uses it for BASELINE configs[2].)
+* row bands of ONE image — rank r owns global rows [r*H/G, (r+1)*H/G).  Two exchange steps:
+     1. halo rows: window/2 + 2 input rows from each neighbour (`exchange_halos`: batched isend/irecv —
+        NCCL P2P over NVLink on GPUs, gloo on CPU tensors in the tests);
+     2. hysteresis label merge: every band exports its first/last row as (label, flags) records
+        (`b200_band_boundary_export`), ONE all-gather (`gather_records`), then every rank unions the records
+        that touch across a boundary and finalises its own band (`b200_band_finalize`).
+  `BandPipeline.run` chains: exchange_halos -> b200_band_front -> export -> all_gather -> finalize.
+
+`canny_bands_virtual` runs the same band kernels for G bands sequentially on ONE GPU (exchange replaced by
+local slicing/concatenation), so the cross-band merge is testable without a multi-GPU box.
+
+All compute is in libcanny_b200.so (sm_100a CUDA); nothing here computes pixels on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from ._lib import check, load
+from .api import Context
+
+RECORD_BYTES = 8  # b200_band_record: int32 label, int32 flags
+
+
+# ---------------------------------------------------------------------------------------------------
+# geometry
+# ---------------------------------------------------------------------------------------------------
+def frame_slice(n_frames: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous block of frames owned by `rank`: (first, count). Remainders go to the low ranks."""
+    base, rem = divmod(n_frames, world)
+    first = rank * base + min(rank, rem)
+    return first, base + (1 if rank < rem else 0)
+
+
+@dataclass(frozen=True)
+class BandGeometry:
+    rank: int
+    world: int
+    height: int       # global image height
+    width: int
+    row0: int         # first global row owned
+    rows: int         # rows owned
+    halo: int         # rows needed beyond an interior band edge (window/2 + 2)
+    halo_above: int   # rows actually present above (0 at the image top)
+    halo_below: int
+
+    @property
+    def buffer_rows(self) -> int:
+        return self.halo_above + self.rows + self.halo_below
+
+
+def band_geometry(height: int, width: int, rank: int, world: int, sigma: float) -> BandGeometry:
+    """Row band of `rank`. Every band must be at least `halo` rows tall so a halo comes from ONE neighbour."""
+    halo = int(load().b200_band_halo_rows(C.c_float(sigma)))
+    base, rem = divmod(height, world)
+    row0 = rank * base + min(rank, rem)
+    rows = base + (1 if rank < rem else 0)
+    if world > 1 and base < max(halo, 2):
+        raise ValueError(f"bands of {base} rows are shorter than the {halo}-row halo; use fewer ranks")
+    above = min(halo, row0)
+    below = min(halo, height - (row0 + rows))
+    return BandGeometry(rank, world, height, width, row0, rows, halo, above, below)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the two exchange steps (device-agnostic torch code: NCCL on GPUs, gloo on CPU tensors)
+# ---------------------------------------------------------------------------------------------------
+def exchange_halos(band, geo: BandGeometry, group=None):
+    """band: uint8 tensor (geo.rows, W) owned by this rank.  Returns a (geo.buffer_rows, W) tensor
+    [halo from rank-1 | band | halo from rank+1] on the same device.  One batched isend/irecv round."""
+    import torch
+    import torch.distributed as dist
+
+    W = geo.width
+    buf = torch.empty((geo.buffer_rows, W), dtype=torch.uint8, device=band.device)
+    buf[geo.halo_above:geo.halo_above + geo.rows].copy_(band)
+    if geo.world == 1:
+        return buf
+    ops = []
+    up, down = geo.rank - 1, geo.rank + 1
+    # what the neighbours need from me is THEIR halo size, which equals geo.halo for interior edges
+    send_up = band[:geo.halo].contiguous() if up >= 0 else None
+    send_down = band[geo.rows - geo.halo:].contiguous() if down < geo.world else None
+    recv_up = buf[:geo.halo_above] if up >= 0 else None
+    recv_down = buf[geo.halo_above + geo.rows:] if down < geo.world else None
+    if up >= 0:
+        ops.append(dist.P2POp(dist.isend, send_up, up, group))
+        ops.append(dist.P2POp(dist.irecv, recv_up, up, group))
+    if down < geo.world:
+        ops.append(dist.P2POp(dist.isend, send_down, down, group))
+        ops.append(dist.P2POp(dist.irecv, recv_down, down, group))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    return buf
+
+
+def gather_records(records, world: int, group=None):
+    """records: uint8 tensor of this band's boundary records (n_records*8 bytes).  Returns all bands'
+    records concatenated in band order (world*n_records*8 bytes) — the hysteresis path's one collective."""
+    import torch
+    import torch.distributed as dist
+
+    if world == 1:
+        return records
+    out = torch.empty((world * records.numel(),), dtype=torch.uint8, device=records.device)
+    dist.all_gather_into_tensor(out, records.contiguous(), group=group)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# band pipeline on one rank
+# ---------------------------------------------------------------------------------------------------
+class BandPipeline:
+    """Canny of one row band of a larger image on this rank's GPU."""
+
+    def __init__(self, ctx: Context, height: int, width: int, rank: int, world: int, sigma: float, min_val: int,
+                 max_val: int, group=None):
+        self.ctx, self.group = ctx, group
+        self.sigma, self.lo, self.hi = float(sigma), int(min_val), int(max_val)
+        self.geo = band_geometry(height, width, rank, world, sigma)
+        self.lib = load()
+        self.n_records = int(self.lib.b200_band_record_count(width))
+
+    def front(self, buf, edges) -> None:
+        g = self.geo
+        check(self.lib.b200_band_front(self.ctx.handle, buf.data_ptr(), g.halo_above, g.halo_below, g.rows, g.row0, g.height,
+                                       g.width, C.c_float(self.sigma), self.lo, self.hi, edges.data_ptr()))
+
+    def export(self, records) -> None:
+        check(self.lib.b200_band_boundary_export(self.ctx.handle, self.geo.rows, self.geo.width, records.data_ptr()))
+
+    def finalize(self, all_records, edges) -> None:
+        g = self.geo
+        check(self.lib.b200_band_finalize(self.ctx.handle, all_records.data_ptr(), g.world, g.rank, g.rows, g.width, edges.data_ptr()))
+
+    def run(self, band, edges=None):
+        """band: (rows, W) uint8 CUDA tensor (this rank's rows).  Returns the (rows, W) uint8 0/255 edge band.
+        Work is issued on torch's current stream (the context is pointed at it), so NCCL ordering is the
+        stream's ordering."""
+        import torch
+
+        g = self.geo
+        self.ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        if edges is None:
+            edges = torch.empty((g.rows, g.width), dtype=torch.uint8, device=band.device)
+        buf = exchange_halos(band, g, self.group)
+        self.front(buf, edges)
+        records = torch.empty((self.n_records * RECORD_BYTES,), dtype=torch.uint8, device=band.device)
+        self.export(records)
+        all_records = gather_records(records, g.world, self.group)
+        self.finalize(all_records, edges)
+        return edges
+
+
+def canny_bands_virtual(img: np.ndarray, n_bands: int, sigma: float, min_val: int, max_val: int, device: int = 0) -> np.ndarray:
+    """All bands of one image on ONE GPU, sequentially, through the same band kernels (one context per band,
+    because a context keeps its band's label state between front/export/finalize).  The two exchanges become
+    local slicing and concatenation.  Returns the (H, W) uint8 0/255 map."""
+    import torch
+
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    H, W = img.shape
+    dev = torch.device("cuda", device)
+    d_img = torch.from_numpy(img).to(dev)
+    ctxs: List[Context] = [Context(device) for _ in range(n_bands)]
+    try:
+        pipes = [BandPipeline(ctxs[b], H, W, b, n_bands, sigma, min_val, max_val) for b in range(n_bands)]
+        edges, recs = [], []
+        for p in pipes:
+            g = p.geo
+            buf = d_img[g.row0 - g.halo_above:g.row0 + g.rows + g.halo_below].contiguous()
+            e = torch.empty((g.rows, W), dtype=torch.uint8, device=dev)
+            p.front(buf, e)
+            r = torch.empty((p.n_records * RECORD_BYTES,), dtype=torch.uint8, device=dev)
+            p.export(r)
+            ctxs[g.rank].synchronize()
+            edges.append(e)
+            recs.append(r)
+        all_records = torch.cat(recs)
+        for p, e in zip(pipes, edges):
+            p.finalize(all_records, e)
+            p.ctx.synchronize()
+        return torch.cat(edges).cpu().numpy()
+    finally:
+        for c in ctxs:
+            c.close()

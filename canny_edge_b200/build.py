@@ -15,8 +15,8 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libcanny_b200.so"
-SOURCES = ["front.cu", "hysteresis.cu", "stages.cu", "synth.cu", "band.cu", "selftest.cu", "api.cu"]
-HEADERS = ["internal.h", "canny_math.h", "ccl.cuh", "exact_math.cuh", "../../include/canny_b200.h"]
+SOURCES = ["front.cu", "front2.cu", "hysteresis.cu", "stages.cu", "synth.cu", "band.cu", "selftest.cu", "api.cu"]
+HEADERS = ["internal.h", "front_common.cuh", "canny_math.h", "ccl.cuh", "exact_math.cuh", "../../include/canny_b200.h"]
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3",

@@ -104,6 +104,8 @@ int prepare_gauss(b200_ctx* ctx, float sigma) {
         for (float v : g.w) wmin = v < wmin ? v : wmin;
         g.tiny = !((double)wmin * (double)wmin >= 8.077935669463161e-28);  // 2^-90
     }
+    g.div3_ok = false;
+    if (!g.tiny) CB_TRY(check_div3_device(ctx, g.count[0], g.count[(size_t)n1 * n1], &g.div3_ok));
     g.sigma = sigma;
     g.window = window;
     g.radius = radius;

@@ -27,6 +27,7 @@
 #include "canny_math.h"
 #include "exact_math.cuh"
 #include "internal.h"
+#include "front_common.cuh"
 
 namespace cb {
 
@@ -72,76 +73,6 @@ __host__ __device__ inline SmemLayout smem_layout(int radius) {
     L.bar_off = o;  o += 2 * 8;
     L.total = o;
     return L;
-}
-
-// ---------------------------------------------------------------------------------------------
-// small PTX wrappers (mbarrier + TMA)
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a TMA that never lands (bad descriptor) must become an error, not a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    for (int spin = 0; spin < (1 << 26); ++spin)
-        if (mbar_try_wait(bar, parity)) return;
-    __trap();
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y, int z) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y), "r"(z)
-        : "memory");
-}
-
-// u8 -> f32 without the conversion pipe: drop the byte into the mantissa of 2^23 and subtract 2^23.
-template <int BYTE>
-__device__ __forceinline__ float byte_to_float(uint32_t word) {
-    uint32_t bits = __byte_perm(word, 0x4B000000u, 0x7650 + BYTE);  // {b, 0x00, 0x00, 0x4B}
-    return __fsub_rn(__uint_as_float(bits), 8388608.0f);
-}
-__device__ __forceinline__ float byte_to_float_dyn(const uint32_t* words, int i) {
-    uint32_t word = words[i >> 2];
-    uint32_t bits = __byte_perm(word, 0x4B000000u, 0x7650 + (i & 3));
-    return __fsub_rn(__uint_as_float(bits), 8388608.0f);
-}
-
-// The shared blur core.  S consecutive outputs o = 0..S-1; output o is
-//     ((x[o]*w[0] + x[o+1]*w[1]) + ... ) + x[o+2R]*w[2R]          (ascending taps, RN after every op)
-// exactly as src/utils.cpp:41-46 / 56-61.  ws[j] = w[R+j] = w[R-j].
-template <int R, int S, typename Fetch, typename Emit>
-__device__ __forceinline__ void blur_run(const float (&ws)[R + 1], Fetch fetch, Emit emit) {
-    float acc[S];
-#pragma unroll
-    for (int i = 0; i < S + 2 * R; ++i) {
-        const float x = fetch(i);
-        float q[R + 1];
-#pragma unroll
-        for (int j = 0; j <= R; ++j) q[j] = __fmul_rn(x, ws[j]);  // unused ones are dead code
-#pragma unroll
-        for (int t = 0; t <= 2 * R; ++t) {
-            const int o = i - t;
-            if (o >= 0 && o < S) {
-                const int j = t < R ? R - t : t - R;
-                acc[o] = (t == 0) ? q[j] : __fadd_rn(acc[o], q[j]);  // 0 + q == q exactly
-            }
-        }
-        if (i >= 2 * R) emit(i - 2 * R, acc[i - 2 * R]);
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -568,39 +499,40 @@ int choose_bands(const b200_ctx* ctx, int out_rows, int strips, int frames, int 
     return bands;
 }
 
-int launch_front(b200_ctx* ctx, cudaStream_t st, const FrontParams& p_in) {
-    FrontParams p = p_in;
-    p.ieee_div = ctx->gauss.tiny ? 1 : 0;
-    const int radius = p.radius;
-    if (radius < 1 || radius > B200_MAX_RADIUS) {
-        set_error("gaussian radius %d outside [1,%d]", radius, B200_MAX_RADIUS);
-        return B200_ERR_UNSUPPORTED;
+// Builds the 3-D u8 tensor map {width, rows in the buffer, frames} with a box of box_cols x box_rows x 1.  TMA needs a
+// 16 B aligned base and row pitch; *use_tma is false when the image does not qualify (the kernels then run their
+// generic staging variant — same kernel, byte loads instead of the bulk copy).
+int make_input_tensor_map(const FrontParams& p, int box_cols, int box_rows, CUtensorMap* tmap, bool* use_tma) {
+    static const bool tma_env_off = [] { const char* e = getenv("B200_CANNY_NO_TMA"); return e && e[0] == '1'; }();
+    memset(tmap, 0, sizeof(*tmap));
+    *use_tma = !tma_env_off && (p.width % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.in) & 15) == 0) &&
+               (p.in_frame_stride % 16 == 0) && get_encode_fn() != nullptr;
+    if (!*use_tma) return B200_OK;
+    const cuuint64_t dims[3] = {(cuuint64_t)p.width, (cuuint64_t)p.in_rows, (cuuint64_t)p.n_frames};
+    const cuuint64_t strides[2] = {(cuuint64_t)p.width, (cuuint64_t)p.in_frame_stride};
+    const cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = get_encode_fn()(tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(p.in), dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for %dx%dx%d", (int)r, p.width, p.in_rows, p.n_frames);
+        return B200_ERR_CUDA;
     }
+    return B200_OK;
+}
+
+static int launch_front_v1(b200_ctx* ctx, cudaStream_t st, const FrontParams& p_in) {
+    FrontParams p = p_in;
+    const int radius = p.radius;
     const int strips = (p.width + kTW - 1) / kTW;
     p.tiles_x = strips;
     if (p.tiles_y <= 0) p.tiles_y = choose_bands(ctx, p.out_rows, strips, p.n_frames, radius);
     dim3 grid(strips, p.tiles_y, p.n_frames);
     const bool spill = p.blur || p.mag || p.ang || p.nms;
-
-    // TMA needs a 16 B aligned base and row pitch; otherwise the generic staging variant of the same kernel runs.
-    static const bool tma_env_off = [] { const char* e = getenv("B200_CANNY_NO_TMA"); return e && e[0] == '1'; }();
-    bool use_tma = !tma_env_off && (p.width % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.in) & 15) == 0) &&
-                   (p.in_frame_stride % 16 == 0) && get_encode_fn() != nullptr;
     CUtensorMap tmap;
-    memset(&tmap, 0, sizeof(tmap));
-    if (use_tma) {
-        const cuuint64_t dims[3] = {(cuuint64_t)p.width, (cuuint64_t)p.in_rows, (cuuint64_t)p.n_frames};
-        const cuuint64_t strides[2] = {(cuuint64_t)p.width, (cuuint64_t)p.in_frame_stride};
-        const cuuint32_t box[3] = {(cuuint32_t)in_pitch_for(radius), (cuuint32_t)kSlab, 1};
-        const cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = get_encode_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(p.in), dims, strides, box,
-                                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            set_error("cuTensorMapEncodeTiled failed (%d) for %dx%dx%d", (int)r, p.width, p.in_rows, p.n_frames);
-            return B200_ERR_CUDA;
-        }
-    }
+    bool use_tma = false;
+    CB_TRY(make_input_tensor_map(p, in_pitch_for(radius), kSlab, &tmap, &use_tma));
     switch (radius) {
         case 2: return launch_r<2>(ctx, st, p, tmap, grid, use_tma, spill);
         case 3: return launch_r<3>(ctx, st, p, tmap, grid, use_tma, spill);
@@ -610,6 +542,22 @@ int launch_front(b200_ctx* ctx, cudaStream_t st, const FrontParams& p_in) {
         case 15: return launch_r<15>(ctx, st, p, tmap, grid, use_tma, spill);
         default: return launch_r<0>(ctx, st, p, tmap, grid, use_tma, spill);
     }
+}
+
+// Dispatcher: the lean kernel (front2.cu) for the hot configuration — compile-time radius, no spill planes,
+// ordinary sigma; front_kernel above for everything else.  B200_CANNY_FRONT=1 forces the first kernel (A/B runs).
+int launch_front(b200_ctx* ctx, cudaStream_t st, const FrontParams& p_in) {
+    FrontParams p = p_in;
+    p.ieee_div = ctx->gauss.tiny ? 1 : 0;
+    const int radius = p.radius;
+    if (radius < 1 || radius > B200_MAX_RADIUS) {
+        set_error("gaussian radius %d outside [1,%d]", radius, B200_MAX_RADIUS);
+        return B200_ERR_UNSUPPORTED;
+    }
+    static const bool force_v1 = [] { const char* e = getenv("B200_CANNY_FRONT"); return e && e[0] == '1'; }();
+    const bool spill = p.blur || p.mag || p.ang || p.nms;
+    if (!force_v1 && !spill && !ctx->gauss.tiny && front2_supports(radius)) return launch_front2(ctx, st, p);
+    return launch_front_v1(ctx, st, p);
 }
 
 }  // namespace cb

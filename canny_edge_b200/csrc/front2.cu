@@ -1,0 +1,479 @@
+// front2.cu — the lean fused front kernel: u8 gray -> u8 class map (0 / 1 weak / 255 strong) for sm_100a.
+//
+// Same contract and the same arithmetic as front.cu's front_kernel (stages 1-3 of the reference's CPU path,
+// src/utils.cpp:26-68,106-187,201-236,248-308 + the two thresholds of :327-340), restructured so that the
+// per-pixel instruction count is close to the arithmetic the reference's rounding order makes unavoidable
+// (profiles/r01_front_opcode_mix.txt: the first kernel spent 76 % of its issue slots on integer addressing,
+// predicates and branches).  Differences in structure, not in results:
+//
+//   * slabs of 64 rows x 128 columns, one TMA box each, double buffered (mbarrier complete_tx);
+//   * every intermediate sits in a LINEAR shared-memory buffer whose tail rows are copied to the head once per
+//     slab, so all addresses inside the unrolled blur runs are base + compile-time immediate;
+//   * runs of 32 outputs per thread (register sliding window, symmetric-weight product sharing);
+//   * the column pass also does the vertical half of Sobel in registers and stores ONE packed word per pixel,
+//     (u << 16) + v with  v = B[r-1] + 2B[r] + B[r+1]  and  u = B[r+1] - B[r-1],  so the last phase gets
+//     gx = v[c+1] - v[c-1] and gy = u[c-1] + 2u[c] + u[c+1] from three packed integer adds;
+//   * image borders are handled by uniform (per-CTA / per-run) variants, never per pixel in the hot path;
+//   * magnitude^2 is compared against the squared thresholds; direction, the exact integer square root and the
+//     neighbour magnitudes are only evaluated for candidate pixels (n >= minVal^2).
+//
+// Used for compile-time radii without spill planes; everything else (run-time radius, `steps` planes, sigma so
+// small that sums approach the subnormal range) stays on front.cu's kernel.
+#include <cuda.h>
+
+#include "canny_math.h"
+#include "exact_math.cuh"
+#include "front_common.cuh"
+#include "internal.h"
+
+namespace cb {
+namespace f2 {
+
+constexpr int kThreads = 256;
+constexpr int kSlab = 64;        // rows per marching step (one TMA box)
+constexpr int kTC = 128;         // computed columns per strip (temp / VU lines); column j <-> image x = x0 - 2 + j
+constexpr int kTW = kTC - 4;     // class-map columns produced per strip (Sobel + NMS eat 2 per side)
+constexpr int kTempPitch = 132;  // floats; == 4 mod 32: the row pass's 128-bit stores (lane = row) hit 8 distinct bank groups
+constexpr int kVuPitch = 132;    // int32 words; lane 31 of the last phase reads 4 words past column 127
+constexpr int kRunRow = 32;      // outputs per thread in the row pass
+constexpr int kRunCol = 34;      // blurred rows per thread in the column pass (32 VU rows need 34 blurred rows)
+
+__host__ __device__ constexpr int in_pitch_for(int radius) {
+    // bytes per staged input row: up to 15 leading bytes (the TMA box starts on a 16 B boundary of the image
+    // row), 128 + 2R needed ones; a multiple of 16 (TMA) and an ODD multiple so lane = row 128-bit loads spread
+    // over 8 distinct bank groups
+    int k = (15 + kTC + 2 * radius + 15) / 16;
+    if ((k & 1) == 0) k += 1;
+    return 16 * k;
+}
+__host__ __device__ constexpr int temp_rows_for(int radius) { return kSlab + 2 * radius + 2; }
+constexpr int kVuRows = kSlab + 2;
+
+struct SmemLayout {
+    int in_off, temp_off, vu_off, tab_off, w_off, bar_off, total;
+};
+__host__ __device__ constexpr SmemLayout smem_layout(int radius) {
+    SmemLayout L{};
+    int o = 0;
+    L.in_off = o;   o += 2 * kSlab * in_pitch_for(radius);
+    o = (o + 127) & ~127;
+    L.temp_off = o; o += temp_rows_for(radius) * kTempPitch * 4;
+    L.vu_off = o;   o += kVuRows * kVuPitch * 4;
+    L.tab_off = o;  o += 2 * (radius + 1) * (radius + 1) * 4;  // count table, reciprocal table
+    L.w_off = o;    o += (2 * radius + 1) * 4;
+    o = (o + 15) & ~15;
+    L.bar_off = o;  o += 2 * 8;
+    L.total = o;
+    return L;
+}
+
+// RN(a / b) for the interior count: y = RN(1/b).  DIV3 is only instantiated when the host has checked, for this
+// very b and every float mantissa, that one Markstein correction already gives the IEEE quotient.
+template <bool DIV3>
+__device__ __forceinline__ float div_const(float a, float b, float y) {
+    if (DIV3) {
+        const float q = __fmul_rn(a, y);
+        const float r = __fmaf_rn(-b, q, a);
+        return __fmaf_rn(r, y, q);
+    }
+    return div_exact(a, b, y);
+}
+
+// (short)(q) of src/utils.cpp:62 for 0 <= q < 2^22 without the conversion pipe: adding 2^23 with round-toward-zero
+// leaves 2^23 + trunc(q) exactly, i.e. the integer sits in the low mantissa bits.  Returns 0x4B000000 + trunc(q).
+__device__ __forceinline__ int trunc_biased(float q) { return __float_as_int(__fadd_rz(q, 8388608.0f)); }
+constexpr int kBias = 0x4B000000;
+constexpr int kBias4 = (int)(4u * 0x4B000000u);  // 4 * bias mod 2^32 = 0x2C000000
+
+template <int R, bool USE_TMA, bool DIV3>
+__global__ void __launch_bounds__(kThreads, 2)
+front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr SmemLayout L = smem_layout(R);
+    constexpr int in_pitch = in_pitch_for(R);
+    constexpr int T0 = 2 * R + 2;  // temp buffer row of the first row of the current slab
+
+    unsigned char* s_in = smem + L.in_off;
+    float* s_temp = reinterpret_cast<float*>(smem + L.temp_off);
+    int32_t* s_vu = reinterpret_cast<int32_t*>(smem + L.vu_off);
+    float* s_cnt = reinterpret_cast<float*>(smem + L.tab_off);
+    float* s_rcp = s_cnt + (R + 1) * (R + 1);
+    float* s_w = reinterpret_cast<float*>(smem + L.w_off);
+    const uint32_t bar0 = smem_u32(smem + L.bar_off);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+
+    // ---- which strip / band / frame ----
+    const int strip = blockIdx.x, band = blockIdx.y, frame = blockIdx.z;
+    const int x0 = strip * kTW;
+    const int rows_per_band = (p.out_rows + p.tiles_y - 1) / p.tiles_y;
+    const int yb = p.out_row0 + band * rows_per_band;
+    const int ye = min(p.out_row0 + p.out_rows, yb + rows_per_band);
+    if (yb >= ye) return;
+    const int W = p.width, H = p.height;
+    const int n_slabs = (ye - yb + 2 * R + 4 + kSlab - 1) / kSlab;
+    const int in_y0 = yb - 2 - R;                 // global row of slab 0, line 0
+    const int lead = (x0 - 2 - R) & 15;           // bytes between the 16 B aligned box origin and the first needed column
+    const int in_x0 = x0 - 2 - R - lead;          // global column of staged byte 0 (a multiple of 16, may be negative)
+
+    for (int i = tid; i < (R + 1) * (R + 1); i += kThreads) {
+        s_cnt[i] = p.count[i];
+        s_rcp[i] = p.count[(R + 1) * (R + 1) + i];
+    }
+    for (int i = tid; i < 2 * R + 1; i += kThreads) s_w[i] = p.w[i];
+    if (USE_TMA && tid == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    float ws[R + 1];
+#pragma unroll
+    for (int j = 0; j <= R; ++j) ws[j] = s_w[R + j];
+    const float cnt_full = s_cnt[0], rcp_full = s_rcp[0];
+    // strips whose every computed column has all its taps inside the image divide by the constant count
+    const bool x_interior = (x0 - 2 - R >= 0) && (x0 - 2 + kTC - 1 + R <= W - 1);
+    // strips that contain image column -1 or W need the virtual Sobel columns patched in (see the patch pass)
+    const bool x_edge = (x0 - 2 < 0) || (x0 - 2 + kTC - 1 >= W);
+
+    const uint8_t* in_frame = p.in + (long long)frame * p.in_frame_stride;
+    constexpr uint32_t slab_bytes = (uint32_t)(kSlab * in_pitch);
+
+    auto issue_slab = [&](int k) {
+        const int gy = in_y0 + k * kSlab;
+        unsigned char* dst = s_in + (k & 1) * slab_bytes;
+        if (USE_TMA) {
+            if (tid == 0) {
+                const uint32_t bar = bar0 + 8 * (k & 1);
+                mbar_expect_tx(bar, slab_bytes);
+                tma_load_3d(smem_u32(dst), &tmap, bar, in_x0, gy - p.in_row0, frame);
+            }
+        } else {
+            // generic staging (image pitch not a multiple of 16 B): byte loads, zero outside the image / buffer
+            for (int i = tid; i < kSlab * in_pitch; i += kThreads) {
+                const int r = i / in_pitch, c = i - r * in_pitch;
+                const int y = gy + r, x = in_x0 + c;
+                const int by = y - p.in_row0;
+                unsigned char v = 0;
+                if (y >= 0 && y < H && by >= 0 && by < p.in_rows && x >= 0 && x < W) v = in_frame[(long long)by * W + x];
+                dst[i] = v;
+            }
+        }
+    };
+
+    if (USE_TMA) {
+        issue_slab(0);
+        if (n_slabs > 1) issue_slab(1);
+    }
+
+    for (int k = 0; k < n_slabs; ++k) {
+        const int I_k = in_y0 + k * kSlab;  // global row of this slab's first input line
+        if (USE_TMA) {
+            mbar_wait(bar0 + 8 * (k & 1), (uint32_t)((k >> 1) & 1));
+        } else {
+            issue_slab(k);
+            __syncthreads();
+        }
+        const unsigned char* slab = s_in + (k & 1) * slab_bytes;
+
+        // ===================== phase 1: row blur, u8 -> f32 (src/utils.cpp:37-49) =====================
+        // thread = (slab row 32*(warp>>2) + lane, 32 columns starting at 32*(warp&3)); temp buffer row T0 + slab row
+        {
+            const int srow = 32 * (warp >> 2) + lane;
+            const int seg = warp & 3;
+            // needed bytes of this line: [32*seg + lead, 32*seg + lead + 32 + 2R).  lead = 4*dq + DR with DR a compile-time
+            // constant (x0 is a multiple of 4) and dq uniform over the CTA: load aligned 128-bit vectors, shift by dq
+            // WORDS with a uniform switch, pick bytes with static selectors.
+            constexpr int DR = (((-2 - R) % 4) + 4) % 4;
+            constexpr int KW = (DR + kRunRow + 2 * R + 3) / 4;   // words holding the needed bytes
+            constexpr int NV = (KW + 3 + 3) / 4;                 // vectors covering KW + 3 words
+            static_assert(32 * 3 + 16 * NV <= in_pitch, "row pass would read past the staged line");
+            uint32_t wv[NV * 4];
+            const uint4* src = reinterpret_cast<const uint4*>(slab + srow * in_pitch + seg * kRunRow);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const uint4 t4 = src[v];
+                wv[4 * v + 0] = t4.x; wv[4 * v + 1] = t4.y; wv[4 * v + 2] = t4.z; wv[4 * v + 3] = t4.w;
+            }
+            uint32_t w2[KW];
+            switch (lead >> 2) {
+                case 0:
+#pragma unroll
+                    for (int q = 0; q < KW; ++q) w2[q] = wv[q];
+                    break;
+                case 1:
+#pragma unroll
+                    for (int q = 0; q < KW; ++q) w2[q] = wv[q + 1];
+                    break;
+                case 2:
+#pragma unroll
+                    for (int q = 0; q < KW; ++q) w2[q] = wv[q + 2];
+                    break;
+                default:
+#pragma unroll
+                    for (int q = 0; q < KW; ++q) w2[q] = wv[q + 3];
+                    break;
+            }
+            float* trow = s_temp + (T0 + srow) * kTempPitch + seg * kRunRow;
+            const int gx_first = x0 - 2 + seg * kRunRow;  // image column of output 0
+            float grp[4];
+            blur_run<R, kRunRow>(
+                ws,
+                [&](int i) {
+                    const uint32_t word = w2[(i + DR) >> 2];
+                    const uint32_t bits = __byte_perm(word, 0x4B000000u, 0x7650 + ((i + DR) & 3));  // {byte, 0, 0, 0x4B} = 2^23 + byte
+                    return __fsub_rn(__uint_as_float(bits), 8388608.0f);
+                },
+                [&](int o, float s) {
+                    grp[o & 3] = s;
+                    if ((o & 3) == 3) {
+                        // divide by the in-image weight sum (src/utils.cpp:47) and store four outputs
+                        if (x_interior) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) grp[e] = div_const<DIV3>(grp[e], cnt_full, rcp_full);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int gx = gx_first + (o - 3) + e;
+                                if (gx < 0 || gx >= W) { grp[e] = 0.f; continue; }
+                                const int a = max(0, R - gx), b = max(0, gx + R - (W - 1));
+                                const int ti = a * (R + 1) + b;
+                                grp[e] = div_exact(grp[e], s_cnt[ti], s_rcp[ti]);
+                            }
+                        }
+                        *reinterpret_cast<float4*>(trow + (o - 3)) = make_float4(grp[0], grp[1], grp[2], grp[3]);
+                    }
+                });
+        }
+        __syncthreads();  // (A) this slab's temp lines are complete; staged buffer k&1 is free again
+        if (USE_TMA && k + 2 < n_slabs) issue_slab(k + 2);
+
+        // ===================== phase 2: column blur f32 -> int (src/utils.cpp:52-64) + vertical half of Sobel =====================
+        // thread = (column tid&127, half tid>>7).  Blurred rows Bg(o) = I_k - R - 2 + 32*half + o, o = 0..33, from temp buffer
+        // rows 32*half + o .. + 2R; VU rows Bg(1..32) go to VU buffer rows 2 + 32*half + (o-2).
+        {
+            const int c = tid & (kTC - 1);
+            const int half = tid >> 7;
+            const float* tcol = s_temp + (32 * half) * kTempPitch + c;
+            int32_t* vcol = s_vu + (2 + 32 * half) * kVuPitch + c;
+            const int bg0 = I_k - R - 2 + 32 * half;  // global row of blurred output 0
+            // interior run: every blurred row has all 2R+1 taps inside the image, and every VU row has both vertical neighbours
+            const bool y_interior = (bg0 - R >= 0) && (bg0 + kRunCol - 1 + R <= H - 1);
+            int t0 = 0, t1 = 0;  // biased blurred values of rows o-2, o-1
+            if (y_interior) {
+                blur_run<R, kRunCol>(
+                    ws, [&](int i) { return tcol[i * kTempPitch]; },
+                    [&](int o, float s) {
+                        const int t2 = trunc_biased(div_const<DIV3>(s, cnt_full, rcp_full));
+                        if (o >= 2) {
+                            const int u = t2 - t0;                        // B[r+1] - B[r-1]
+                            const int v4 = t0 + 2 * t1 + t2 - kBias4;     // B[r-1] + 2 B[r] + B[r+1]
+                            vcol[(o - 2) * kVuPitch] = (u << 16) + v4;
+                        }
+                        t0 = t1; t1 = t2;
+                    });
+            } else {
+                // border run: per-row counts, rows outside the image, replicate / drop rules of src/utils.cpp:117-184
+                blur_run<R, kRunCol>(
+                    ws, [&](int i) { return tcol[i * kTempPitch]; },
+                    [&](int o, float s) {
+                        const int gy = bg0 + o;
+                        int t2 = kBias;
+                        if (gy >= 0 && gy < H) {
+                            const int a = max(0, R - gy), b = max(0, gy + R - (H - 1));
+                            const int ti = a * (R + 1) + b;
+                            t2 = trunc_biased(div_exact(s, s_cnt[ti], s_rcp[ti]));
+                        }
+                        if (o >= 2) {
+                            const int r = gy - 1;  // the VU row: blurred rows r-1 (t0), r (t1), r+1 (t2)
+                            int word = 0;
+                            if (r >= 0 && r < H) {
+                                const int bm = t0 - kBias, bc = t1 - kBias, bp = t2 - kBias;
+                                const int up = (r > 0) ? bm : bc, dn = (r < H - 1) ? bp : bc;          // vertical replicate (gy term)
+                                const int u = dn - up;
+                                const int v = 2 * bc + ((r > 0) ? bm : 0) + ((r < H - 1) ? bp : 0);    // vertical drop (gx term)
+                                word = (u << 16) + v;
+                            }
+                            vcol[(o - 2) * kVuPitch] = word;
+                        }
+                        t0 = t1; t1 = t2;
+                    });
+            }
+        }
+        __syncthreads();  // (B) VU rows 2..65 complete; every read of the temp buffer is done
+
+        // keep the last 2R+2 temp lines for the next slab (rows 64.. -> rows 0..): disjoint source / destination
+        if (k + 1 < n_slabs) {
+            constexpr int n4 = T0 * (kTC / 4);
+            for (int i = tid; i < n4; i += kThreads) {
+                const int r = i / (kTC / 4), q = i - r * (kTC / 4);
+                reinterpret_cast<float4*>(s_temp + r * kTempPitch)[q] = reinterpret_cast<const float4*>(s_temp + (kSlab + r) * kTempPitch)[q];
+            }
+        }
+        // strips that contain image column -1 or W: the reference replicates horizontally for gx and drops for gy
+        // (src/utils.cpp:117-147 vs :158-184).  gx only reads the v half of a neighbour word and gy only the u half, so ONE
+        // virtual word {v = v[edge], u = 0} in the out-of-image column serves both.  (Uniform branch: the barrier is legal.)
+        if (x_edge) {
+            for (int r = tid; r < kSlab; r += kThreads) {
+                int32_t* row = s_vu + (2 + r) * kVuPitch;
+                if (x0 - 2 < 0) row[1] = row[2] & 0xFFFF;                       // x0 == 0: column j=1 is x=-1, j=2 is x=0
+                const int jw = W - (x0 - 2);                                    // column index of image x = W
+                if (jw >= 1 && jw < kTC) row[jw] = row[jw - 1] & 0xFFFF;
+            }
+            __syncthreads();
+        }
+
+        // ===================== phase 3: horizontal half of Sobel, magnitude^2, NMS, thresholds =====================
+        // class rows y = I_k - R - 2 + rr, rr = 0..63 (VU buffer rows rr, rr+1, rr+2); thread = 4 consecutive pixels
+        {
+            const int y_base = I_k - R - 2;
+            for (int rr = warp; rr < kSlab; rr += kThreads / 32) {
+                const int y = y_base + rr;
+                if (y < yb || y >= ye) continue;                 // uniform per warp
+                const int xw = x0 + 4 * lane;
+                const int32_t* vrow = s_vu + (rr + 1) * kVuPitch + 4 * lane;   // words j = 4*lane .. 4*lane+7; pixel e is j = 4*lane+2+e
+                const int4 qa = *reinterpret_cast<const int4*>(vrow);
+                const int4 qb = *reinterpret_cast<const int4*>(vrow + 4);
+                const int wd[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+                int gxv[4], gyv[4], nv[4];
+                bool any = false;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int wl = wd[e + 1], wc = wd[e + 2], wr = wd[e + 3];
+                    gxv[e] = (int)(short)(wr - wl);              // low halves: v[c+1] - v[c-1] (a borrow only disturbs the high half)
+                    gyv[e] = (wl + wr + 2 * wc) >> 16;           // high halves: u[c-1] + 2u[c] + u[c+1] (low-half sum < 2^16: no carry)
+                    nv[e] = gxv[e] * gxv[e] + gyv[e] * gyv[e];
+                    any |= nv[e] >= p.lo2;
+                }
+                uint32_t cls_word = 0;
+                if (any && lane < kTW / 4) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int n = nv[e];
+                        if (n < p.lo2) continue;
+                        const int x = xw + e;
+                        int cls = p.cls_zero;
+                        const int dir = direction_code<int>(gxv[e], gyv[e]);
+                        // neighbour pair along the quantised direction (src/utils.cpp:253-304)
+                        const int dx = (dir == DIR_90) ? 0 : 1;
+                        const int dy = (dir == DIR_0) ? 0 : ((dir == DIR_45) ? -1 : 1);
+                        // squared magnitude of the neighbour at (y + sy, x + sx), or -1 when it lies outside the image
+                        auto n_at = [&](int sy, int sx) -> int {
+                            const int yy = y + sy, xx = x + sx;
+                            if (yy < 0 || yy >= H || xx < 0 || xx >= W) return -1;
+                            const int32_t* q = s_vu + (rr + 1 + sy) * kVuPitch + 4 * lane + 2 + e + sx;
+                            const int a = q[-1], b = q[0], cc = q[1];
+                            const int g1 = (int)(short)(cc - a), g2 = (a + cc + 2 * b) >> 16;
+                            return g1 * g1 + g2 * g2;
+                        };
+                        const int na = n_at(dy, dx), nb = n_at(-dy, -dx);
+                        if (na < n && nb < n) {
+                            // the reference compares truncated magnitudes: keep iff floor(sqrt(n_nb)) < floor(sqrt(n)) <=> n_nb < mag^2
+                            const int mag = isqrt_floor(n);
+                            const int m2 = mag * mag;
+                            if (na < m2 && nb < m2) cls = (n >= p.hi2) ? 255 : 1;
+                        }
+                        if (x >= W) cls = 0;
+                        cls_word |= (uint32_t)cls << (8 * e);
+                    }
+                }
+                if (lane < kTW / 4 && xw < W) {
+                    const long long o = (long long)frame * p.out_frame_stride + (long long)(y - p.out_row0) * W + xw;
+                    if (((W & 3) == 0) && xw + 3 < W) {
+                        *reinterpret_cast<uint32_t*>(p.cls + o) = cls_word;
+                    } else {
+                        for (int e = 0; e < 4 && xw + e < W; ++e) p.cls[o + e] = (uint8_t)(cls_word >> (8 * e));
+                    }
+                }
+            }
+        }
+        __syncthreads();  // (C) VU reads done; temp tail in place
+        // VU rows 64,65 (blurred-row neighbours of the next slab's first class rows) -> rows 0,1
+        if (k + 1 < n_slabs) s_vu[(tid >> 7) * kVuPitch + (tid & 127)] = s_vu[(kSlab + (tid >> 7)) * kVuPitch + (tid & 127)];
+        // the next iteration's barrier (A) orders this copy before phase 2 rewrites rows 2..65 and phase 3 reads rows 0,1
+    }
+}
+
+}  // namespace f2
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+template <int R, bool USE_TMA, bool DIV3>
+static int launch_one2(b200_ctx* ctx, cudaStream_t st, const FrontParams& p, const CUtensorMap& tmap, dim3 grid) {
+    const f2::SmemLayout L = f2::smem_layout(R);
+    static bool configured[64] = {false};  // per instantiation, per device
+    if (!configured[ctx->device & 63]) {
+        CB_CUDA(cudaFuncSetAttribute(f2::front2_kernel<R, USE_TMA, DIV3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        configured[ctx->device & 63] = true;
+    }
+    {
+        ProfScope ps(ctx, st, 0);
+        f2::front2_kernel<R, USE_TMA, DIV3><<<grid, f2::kThreads, L.total, st>>>(p, tmap);
+    }
+    CB_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return B200_OK;
+}
+
+template <int R>
+static int launch_r2(b200_ctx* ctx, cudaStream_t st, const FrontParams& p, const CUtensorMap& tmap, dim3 grid, bool use_tma, bool div3) {
+    if (use_tma) return div3 ? launch_one2<R, true, true>(ctx, st, p, tmap, grid) : launch_one2<R, true, false>(ctx, st, p, tmap, grid);
+    return div3 ? launch_one2<R, false, true>(ctx, st, p, tmap, grid) : launch_one2<R, false, false>(ctx, st, p, tmap, grid);
+}
+
+bool front2_supports(int radius) {
+    switch (radius) {
+        case 2: case 3: case 5: case 6: case 9: case 15: return true;
+        default: return false;
+    }
+}
+
+// Bands per frame: every band pays 2R+4 warm-up rows and is processed in 64-row slabs, so pick the band count
+// that minimises (slabs per band) x (waves of CTAs) — enough CTAs to fill the machine, few enough that the
+// warm-up and the last partly-filled slab stay small.
+static int choose_bands2(const b200_ctx* ctx, int out_rows, int strips, int frames, int radius) {
+    const int slots = 2 * (ctx->sm_count > 0 ? ctx->sm_count : 148);
+    const long long per_band = (long long)strips * frames;
+    int best = 1;
+    double best_cost = 1e300;
+    const int max_bands = out_rows / f2::kSlab > 0 ? out_rows / f2::kSlab : 1;
+    for (int b = 1; b <= max_bands && b <= 64; ++b) {
+        const int rows = (out_rows + b - 1) / b;
+        const int slabs = (rows + 2 * radius + 4 + f2::kSlab - 1) / f2::kSlab;
+        const long long ctas = per_band * b;
+        const long long waves = (ctas + slots - 1) / slots;
+        const double cost = (double)waves * slabs;  // time ~ waves x slabs per CTA
+        if (cost < best_cost * 0.999) { best_cost = cost; best = b; }
+    }
+    return best;
+}
+
+int launch_front2(b200_ctx* ctx, cudaStream_t st, const FrontParams& p_in) {
+    FrontParams p = p_in;
+    const int radius = p.radius;
+    const int strips = (p.width + f2::kTW - 1) / f2::kTW;
+    p.tiles_x = strips;
+    if (p.tiles_y <= 0) p.tiles_y = choose_bands2(ctx, p.out_rows, strips, p.n_frames, radius);
+    dim3 grid(strips, p.tiles_y, p.n_frames);
+    CUtensorMap tmap;
+    bool use_tma = false;
+    CB_TRY(make_input_tensor_map(p, f2::in_pitch_for(radius), f2::kSlab, &tmap, &use_tma));
+    const bool div3 = ctx->gauss.div3_ok;
+    switch (radius) {
+        case 2: return launch_r2<2>(ctx, st, p, tmap, grid, use_tma, div3);
+        case 3: return launch_r2<3>(ctx, st, p, tmap, grid, use_tma, div3);
+        case 5: return launch_r2<5>(ctx, st, p, tmap, grid, use_tma, div3);
+        case 6: return launch_r2<6>(ctx, st, p, tmap, grid, use_tma, div3);
+        case 9: return launch_r2<9>(ctx, st, p, tmap, grid, use_tma, div3);
+        case 15: return launch_r2<15>(ctx, st, p, tmap, grid, use_tma, div3);
+        default: break;
+    }
+    set_error("front2 kernel not built for radius %d", radius);
+    return B200_ERR_UNSUPPORTED;
+}
+
+}  // namespace cb

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+struct CUtensorMap_st;
+
 #include <string>
 #include <vector>
 
@@ -38,6 +40,8 @@ struct GaussTables {
     float* d_w = nullptr;      // device copies (owned by the context)
     float* d_count = nullptr;
     bool tiny = false;         // min weight^2 < 2^-90: blur sums may approach the subnormal range
+    bool div3_ok = false;      // one Markstein correction already gives RN(a / count_full) for EVERY float mantissa
+                               // (checked exhaustively on the device when the tables are built)
 };
 
 // ---- parameters of the fused front kernel -----------------------------------------------------
@@ -142,6 +146,12 @@ int host_window(float sigma);
 
 // front.cu
 int launch_front(b200_ctx* ctx, cudaStream_t st, const FrontParams& p);
+int make_input_tensor_map(const FrontParams& p, int box_cols, int box_rows, CUtensorMap_st* tmap, bool* use_tma);
+// front2.cu
+bool front2_supports(int radius);
+int launch_front2(b200_ctx* ctx, cudaStream_t st, const FrontParams& p);
+// selftest.cu
+int check_div3_device(b200_ctx* ctx, float b, float y, bool* ok);
 // hysteresis.cu
 int launch_hysteresis(b200_ctx* ctx, cudaStream_t st, const HystParams& p);   // label + resolve
 int launch_ccl_label(b200_ctx* ctx, cudaStream_t st, const HystParams& p);    // tile-local forest + tile-boundary unions

@@ -39,6 +39,35 @@ __global__ void div_check_kernel(const float* __restrict__ cnt, const float* __r
     if (bad) atomicAdd(mismatches, bad);
 }
 
+// every float mantissa a in [1, 2) (the quotient's rounding does not depend on the exponent away from the subnormal
+// range): does ONE Markstein correction already give RN(a / b)?
+__global__ void div3_check_kernel(float b, float y, unsigned long long* __restrict__ mismatches) {
+    unsigned long long bad = 0;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (1u << 23); i += gridDim.x * blockDim.x) {
+        const float a = __uint_as_float(0x3F800000u | i);
+        const float q0 = __fmul_rn(a, y);
+        const float r = __fmaf_rn(-b, q0, a);
+        const float q = __fmaf_rn(r, y, q0);
+        if (__float_as_uint(q) != __float_as_uint(__fdiv_rn(a, b))) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+int check_div3_device(b200_ctx* ctx, float b, float y, bool* ok) {
+    *ok = false;
+    CB_TRY(ensure_ws(ctx->ws_misc, 256));
+    unsigned long long* d = reinterpret_cast<unsigned long long*>(ctx->ws_misc.ptr);
+    unsigned long long h = 1;
+    CB_CUDA(cudaMemsetAsync(d, 0, sizeof(*d), ctx->stream));
+    div3_check_kernel<<<1184, 256, 0, ctx->stream>>>(b, y, d);
+    CB_CUDA(cudaGetLastError());
+    ctx->launches++;
+    CB_CUDA(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *ok = (h == 0);
+    return B200_OK;
+}
+
 }  // namespace cb
 
 using namespace cb;

@@ -49,8 +49,11 @@ __host__ __device__ constexpr int in_pitch_for(int radius) {
 __host__ __device__ constexpr int temp_rows_for(int radius) { return kSlab + 2 * radius + 2; }
 constexpr int kVuRows = kSlab + 2;
 
+constexpr int kNpPitch = 128;    // n-plane words per row: 66 rows x 128 words == the 64 free rows of the temp buffer
+constexpr int kMaxEnt = kSlab * 32;  // candidate list: at most one entry per (class row, lane)
+
 struct SmemLayout {
-    int in_off, temp_off, vu_off, tab_off, w_off, bar_off, total;
+    int in_off, temp_off, vu_off, ent_off, tab_off, w_off, bar_off, total;
 };
 __host__ __device__ constexpr SmemLayout smem_layout(int radius) {
     SmemLayout L{};
@@ -59,13 +62,15 @@ __host__ __device__ constexpr SmemLayout smem_layout(int radius) {
     o = (o + 127) & ~127;
     L.temp_off = o; o += temp_rows_for(radius) * kTempPitch * 4;
     L.vu_off = o;   o += kVuRows * kVuPitch * 4;
+    L.ent_off = o;  o += kMaxEnt * 2;
     L.tab_off = o;  o += 2 * (radius + 1) * (radius + 1) * 4;  // count table, reciprocal table
     L.w_off = o;    o += (2 * radius + 1) * 4;
     o = (o + 15) & ~15;
-    L.bar_off = o;  o += 2 * 8;
+    L.bar_off = o;  o += 2 * 8 + 8;   // two mbarriers + the list counter
     L.total = o;
     return L;
 }
+static_assert(kVuRows * kNpPitch * 4 <= kSlab * kTempPitch * 4, "the n-plane must fit into the free rows of the temp buffer");
 
 // RN(a / b) for the interior count: y = RN(1/b).  DIV3 is only instantiated when the host has checked, for this
 // very b and every float mantissa, that one Markstein correction already gives the IEEE quotient.
@@ -100,6 +105,9 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
     float* s_rcp = s_cnt + (R + 1) * (R + 1);
     float* s_w = reinterpret_cast<float*>(smem + L.w_off);
     const uint32_t bar0 = smem_u32(smem + L.bar_off);
+    int* s_count = reinterpret_cast<int*>(smem + L.bar_off + 16);
+    uint16_t* s_ent = reinterpret_cast<uint16_t*>(smem + L.ent_off);
+    int32_t* s_np = reinterpret_cast<int32_t*>(s_temp + T0 * kTempPitch);   // n-plane: the temp rows phase 1 refills next slab
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -323,74 +331,108 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
                 const int jw = W - (x0 - 2);                                    // column index of image x = W
                 if (jw >= 1 && jw < kTC) row[jw] = row[jw - 1] & 0xFFFF;
             }
-            __syncthreads();
         }
+        if (tid == 0) *s_count = 0;
 
-        // ===================== phase 3: horizontal half of Sobel, magnitude^2, NMS, thresholds =====================
-        // class rows y = I_k - R - 2 + rr, rr = 0..63 (VU buffer rows rr, rr+1, rr+2); thread = 4 consecutive pixels
+        __syncthreads();  // (B2) temp tail saved, virtual columns patched: temp rows T0.. are free, VU rows 0..65 final
+
+        // ===================== phase 3a: horizontal half of Sobel, magnitude^2 plane, candidate list =====================
+        // n-plane row q (0..65) <-> VU buffer row q <-> global row y_base + q - 1; it lives in the free part of the temp buffer.
+        // thread = columns j = 4*lane + 1 + e (e = 0..3) of one row; n[j] is stored at word j-1 so the store is one aligned
+        // 128-bit write.  Class pixels are j = 2..125 of rows q = 1..64; a thread with at least one candidate among its
+        // four pixels appends ONE 16-bit entry {row, lane, 4-bit mask} to the list phase 3b works through densely.
         {
-            const int y_base = I_k - R - 2;
-            for (int rr = warp; rr < kSlab; rr += kThreads / 32) {
-                const int y = y_base + rr;
-                if (y < yb || y >= ye) continue;                 // uniform per warp
-                const int xw = x0 + 4 * lane;
-                const int32_t* vrow = s_vu + (rr + 1) * kVuPitch + 4 * lane;   // words j = 4*lane .. 4*lane+7; pixel e is j = 4*lane+2+e
+            const int y_base = I_k - R - 2;                       // global row of class row rr = 0
+            const uint32_t zero_word = 0x01010101u * (uint32_t)p.cls_zero;
+            const int lane_mask = (lane == 0) ? 0xE : ((lane == 31) ? 0x1 : 0xF);   // j = 1 and j >= 126 are neighbour-only columns
+            for (int q = warp; q < kVuRows; q += kThreads / 32) {
+                const int y = y_base + q - 1;
+                if (y < yb - 1 || y > ye) continue;                // uniform: rows no class row of this band looks at
+                const int32_t* vrow = s_vu + q * kVuPitch + 4 * lane;
                 const int4 qa = *reinterpret_cast<const int4*>(vrow);
-                const int4 qb = *reinterpret_cast<const int4*>(vrow + 4);
-                const int wd[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-                int gxv[4], gyv[4], nv[4];
-                bool any = false;
+                const int2 qb = *reinterpret_cast<const int2*>(vrow + 4);
+                const int wd[6] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y};
+                int nv[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const int wl = wd[e + 1], wc = wd[e + 2], wr = wd[e + 3];
-                    gxv[e] = (int)(short)(wr - wl);              // low halves: v[c+1] - v[c-1] (a borrow only disturbs the high half)
-                    gyv[e] = (wl + wr + 2 * wc) >> 16;           // high halves: u[c-1] + 2u[c] + u[c+1] (low-half sum < 2^16: no carry)
-                    nv[e] = gxv[e] * gxv[e] + gyv[e] * gyv[e];
-                    any |= nv[e] >= p.lo2;
+                    const int wl = wd[e], wc = wd[e + 1], wr = wd[e + 2];
+                    const int gx = (int)(short)(wr - wl);        // low halves: v[c+1] - v[c-1] (a borrow only disturbs the high half)
+                    const int gy = (wl + wr + 2 * wc) >> 16;     // high halves: u[c-1] + 2u[c] + u[c+1] (low-half sum < 2^16: no carry)
+                    nv[e] = gx * gx + gy * gy;
                 }
-                uint32_t cls_word = 0;
-                if (any && lane < kTW / 4) {
+                if (y < 0 || y >= H) {                            // uniform: neighbours outside the image never suppress (src/utils.cpp:253-304)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) nv[e] = -1;
+                }
+                if (x_edge) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const int n = nv[e];
-                        if (n < p.lo2) continue;
-                        const int x = xw + e;
-                        int cls = p.cls_zero;
-                        const int dir = direction_code<int>(gxv[e], gyv[e]);
-                        // neighbour pair along the quantised direction (src/utils.cpp:253-304)
-                        const int dx = (dir == DIR_90) ? 0 : 1;
-                        const int dy = (dir == DIR_0) ? 0 : ((dir == DIR_45) ? -1 : 1);
-                        // squared magnitude of the neighbour at (y + sy, x + sx), or -1 when it lies outside the image
-                        auto n_at = [&](int sy, int sx) -> int {
-                            const int yy = y + sy, xx = x + sx;
-                            if (yy < 0 || yy >= H || xx < 0 || xx >= W) return -1;
-                            const int32_t* q = s_vu + (rr + 1 + sy) * kVuPitch + 4 * lane + 2 + e + sx;
-                            const int a = q[-1], b = q[0], cc = q[1];
-                            const int g1 = (int)(short)(cc - a), g2 = (a + cc + 2 * b) >> 16;
-                            return g1 * g1 + g2 * g2;
-                        };
-                        const int na = n_at(dy, dx), nb = n_at(-dy, -dx);
-                        if (na < n && nb < n) {
-                            // the reference compares truncated magnitudes: keep iff floor(sqrt(n_nb)) < floor(sqrt(n)) <=> n_nb < mag^2
-                            const int mag = isqrt_floor(n);
-                            const int m2 = mag * mag;
-                            if (na < m2 && nb < m2) cls = (n >= p.hi2) ? 255 : 1;
-                        }
-                        if (x >= W) cls = 0;
-                        cls_word |= (uint32_t)cls << (8 * e);
+                        const int x = x0 - 2 + 4 * lane + 1 + e;
+                        if (x < 0 || x >= W) nv[e] = -1;
                     }
                 }
-                if (lane < kTW / 4 && xw < W) {
-                    const long long o = (long long)frame * p.out_frame_stride + (long long)(y - p.out_row0) * W + xw;
-                    if (((W & 3) == 0) && xw + 3 < W) {
-                        *reinterpret_cast<uint32_t*>(p.cls + o) = cls_word;
-                    } else {
-                        for (int e = 0; e < 4 && xw + e < W; ++e) p.cls[o + e] = (uint8_t)(cls_word >> (8 * e));
+                *reinterpret_cast<int4*>(s_np + q * kNpPitch + 4 * lane) = make_int4(nv[0], nv[1], nv[2], nv[3]);
+                if (q >= 1 && q <= kSlab && y >= yb && y < ye) {   // uniform: this row is a class row of the band
+                    int mask = 0;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) mask |= (nv[e] >= p.lo2) ? (1 << e) : 0;
+                    mask &= lane_mask;
+                    const unsigned vote = __ballot_sync(0xffffffffu, mask != 0);
+                    if (vote) {
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(s_count, __popc(vote));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (mask) s_ent[base + __popc(vote & ((1u << lane) - 1u))] = (uint16_t)(((q - 1) << 9) | (lane << 4) | mask);
+                    }
+                    // every class word starts out as "suppressed"; phase 3b overwrites the bytes of surviving pixels
+                    const int xw = x0 + 4 * lane;
+                    if (lane < kTW / 4 && xw < W) {
+                        const long long o = (long long)frame * p.out_frame_stride + (long long)(y - p.out_row0) * W + xw;
+                        if (((W & 3) == 0) && xw + 3 < W) {
+                            *reinterpret_cast<uint32_t*>(p.cls + o) = zero_word;
+                        } else {
+                            for (int e = 0; e < 4 && xw + e < W; ++e) p.cls[o + e] = (uint8_t)p.cls_zero;
+                        }
                     }
                 }
             }
         }
-        __syncthreads();  // (C) VU reads done; temp tail in place
+        __syncthreads();  // (C1) n-plane and candidate list complete; the zero words are ordered before phase 3b's byte stores
+
+        // ===================== phase 3b: direction, NMS and thresholds for the candidates only =====================
+        {
+            const int y_base = I_k - R - 2;
+            const int n_ent = *s_count;
+            for (int i = tid; i < n_ent; i += kThreads) {
+                const int ent = s_ent[i];
+                const int rr = ent >> 9, el = (ent >> 4) & 31, mask = ent & 15;
+                const int y = y_base + rr;
+                uint8_t* orow = p.cls + (long long)frame * p.out_frame_stride + (long long)(y - p.out_row0) * W + (x0 - 2);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (!(mask & (1 << e))) continue;
+                    const int j = 4 * el + 1 + e;
+                    const int32_t* v = s_vu + (rr + 1) * kVuPitch + j;
+                    const int wl = v[-1], wc = v[0], wr = v[1];
+                    const int gx = (int)(short)(wr - wl), gy = (wl + wr + 2 * wc) >> 16;
+                    const int32_t* np = s_np + (rr + 1) * kNpPitch + (j - 1);
+                    const int n = np[0];
+                    const int dir = direction_code<int>(gx, gy);
+                    // neighbour pair along the quantised direction (src/utils.cpp:253-304); out-of-image neighbours hold -1
+                    const int off = (dir == DIR_0) ? 1 : ((dir == DIR_90) ? kNpPitch : ((dir == DIR_45) ? (1 - kNpPitch) : (1 + kNpPitch)));
+                    const int na = np[off], nb = np[-off];
+                    int cls = p.cls_zero;
+                    if (na < n && nb < n) {
+                        // the reference compares truncated magnitudes: keep iff floor(sqrt(n_nb)) < floor(sqrt(n)) <=> n_nb < mag^2
+                        const int mag = isqrt_floor(n);
+                        const int m2 = mag * mag;
+                        if (na < m2 && nb < m2) cls = (n >= p.hi2) ? 255 : 1;
+                    }
+                    if (cls != p.cls_zero) orow[j] = (uint8_t)cls;
+                }
+            }
+        }
+        __syncthreads();  // (C) VU, n-plane and list reads done
         // VU rows 64,65 (blurred-row neighbours of the next slab's first class rows) -> rows 0,1
         if (k + 1 < n_slabs) s_vu[(tid >> 7) * kVuPitch + (tid & 127)] = s_vu[(kSlab + (tid >> 7)) * kVuPitch + (tid & 127)];
         // the next iteration's barrier (A) orders this copy before phase 2 rewrites rows 2..65 and phase 3 reads rows 0,1

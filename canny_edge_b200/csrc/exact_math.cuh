@@ -17,9 +17,14 @@ __device__ __forceinline__ float div_exact(float a, float b, float y) {
     return __fmaf_rn(r, y, q);
 }
 
-// floor(sqrt(n)), 0 <= n < 2^24 here (n <= 2*1020^2): MUFU.SQRT estimate + integer fix-up == (int)sqrt((double)n)
+// floor(sqrt(n)), 0 <= n < 2^24 here (n <= 2*1020^2): ONE MUFU.SQRT estimate + integer fix-up == (int)sqrt((double)n) of
+// src/utils.cpp:212.  sqrt.approx.f32 is within 2^-22 relative, i.e. < 0.001 absolute below 2^12, so the truncated estimate is
+// off by at most one and a single correction in each direction makes it exact (tests/test_gpu_parity.py::test_isqrt_table_device
+// checks every n of the domain).
 __device__ __forceinline__ int isqrt_floor(int n) {
-    int m = (int)sqrtf((float)n);  // compiled without fast-math: correctly rounded; the fix-up keeps it exact regardless
+    float s;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(s) : "f"((float)n));
+    int m = (int)s;
     if (m * m > n) --m;
     if ((m + 1) * (m + 1) <= n) ++m;
     return m;

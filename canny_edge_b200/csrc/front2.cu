@@ -50,7 +50,8 @@ __host__ __device__ constexpr int temp_rows_for(int radius) { return kSlab + 2 *
 constexpr int kVuRows = kSlab + 2;
 
 constexpr int kNpPitch = 128;    // n-plane words per row: 66 rows x 128 words == the 64 free rows of the temp buffer
-constexpr int kMaxEnt = kSlab * 32;  // candidate list: at most one entry per (class row, lane)
+constexpr int kEntPerWarp = (kSlab / 8) * 32;  // candidate list of one warp: at most one entry per (class row of that warp, lane)
+constexpr int kMaxEnt = 8 * kEntPerWarp;
 
 struct SmemLayout {
     int in_off, temp_off, vu_off, ent_off, tab_off, w_off, bar_off, total;
@@ -66,7 +67,7 @@ __host__ __device__ constexpr SmemLayout smem_layout(int radius) {
     L.tab_off = o;  o += 2 * (radius + 1) * (radius + 1) * 4;  // count table, reciprocal table
     L.w_off = o;    o += (2 * radius + 1) * 4;
     o = (o + 15) & ~15;
-    L.bar_off = o;  o += 2 * 8 + 8;   // two mbarriers + the list counter
+    L.bar_off = o;  o += 2 * 8;
     L.total = o;
     return L;
 }
@@ -105,7 +106,6 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
     float* s_rcp = s_cnt + (R + 1) * (R + 1);
     float* s_w = reinterpret_cast<float*>(smem + L.w_off);
     const uint32_t bar0 = smem_u32(smem + L.bar_off);
-    int* s_count = reinterpret_cast<int*>(smem + L.bar_off + 16);
     uint16_t* s_ent = reinterpret_cast<uint16_t*>(smem + L.ent_off);
     int32_t* s_np = reinterpret_cast<int32_t*>(s_temp + T0 * kTempPitch);   // n-plane: the temp rows phase 1 refills next slab
 
@@ -332,103 +332,102 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
                 if (jw >= 1 && jw < kTC) row[jw] = row[jw - 1] & 0xFFFF;
             }
         }
-        if (tid == 0) *s_count = 0;
 
         __syncthreads();  // (B2) temp tail saved, virtual columns patched: temp rows T0.. are free, VU rows 0..65 final
 
-        // ===================== phase 3a: horizontal half of Sobel, magnitude^2 plane, candidate list =====================
+        // ===================== phase 3a: horizontal half of Sobel, magnitude^2 plane, candidate lists =====================
         // n-plane row q (0..65) <-> VU buffer row q <-> global row y_base + q - 1; it lives in the free part of the temp buffer.
         // thread = columns j = 4*lane + 1 + e (e = 0..3) of one row; n[j] is stored at word j-1 so the store is one aligned
-        // 128-bit write.  Class pixels are j = 2..125 of rows q = 1..64; a thread with at least one candidate among its
-        // four pixels appends ONE 16-bit entry {row, lane, 4-bit mask} to the list phase 3b works through densely.
+        // 128-bit write.  Class pixels are j = 2..125 of rows q = 1..64.  A thread with a candidate (n >= minVal^2) among its
+        // four pixels appends ONE 16-bit entry {row, lane} to its WARP's list (no atomics: the count is a warp-uniform
+        // register); phase 3b lets every warp work through its own list with all lanes busy.
+        const int y_base = I_k - R - 2;                           // global row of class row rr = 0
+        int my_count = 0;                                         // entries in this warp's list (uniform over the warp)
+        uint16_t* my_ent = s_ent + warp * kEntPerWarp;
         {
-            const int y_base = I_k - R - 2;                       // global row of class row rr = 0
+            // rows of the n-plane any class row of this band looks at: global rows [max(yb-1, ...), min(ye, ...)]
+            const int q_lo = max(0, yb - y_base), q_hi = min(kVuRows - 1, ye - y_base + 1);   // inclusive, uniform
             const uint32_t zero_word = 0x01010101u * (uint32_t)p.cls_zero;
-            const int lane_mask = (lane == 0) ? 0xE : ((lane == 31) ? 0x1 : 0xF);   // j = 1 and j >= 126 are neighbour-only columns
-            for (int q = warp; q < kVuRows; q += kThreads / 32) {
+            uint8_t* out_lane = p.cls + (long long)frame * p.out_frame_stride + (long long)(y_base - p.out_row0) * W + (x0 + 4 * lane);
+            const bool word_ok = ((W & 3) == 0) && lane < kTW / 4 && (x0 + 4 * lane + 3 < W);  // the aligned 32-bit store applies
+            const bool tail_ok = !word_ok && lane < kTW / 4 && (x0 + 4 * lane < W);            // ragged right edge: byte stores
+            for (int q = warp; q <= q_hi; q += kThreads / 32) {
+                if (q < q_lo) continue;
                 const int y = y_base + q - 1;
-                if (y < yb - 1 || y > ye) continue;                // uniform: rows no class row of this band looks at
-                const int32_t* vrow = s_vu + q * kVuPitch + 4 * lane;
-                const int4 qa = *reinterpret_cast<const int4*>(vrow);
-                const int2 qb = *reinterpret_cast<const int2*>(vrow + 4);
-                const int wd[6] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y};
-                int nv[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int wl = wd[e], wc = wd[e + 1], wr = wd[e + 2];
-                    const int gx = (int)(short)(wr - wl);        // low halves: v[c+1] - v[c-1] (a borrow only disturbs the high half)
-                    const int gy = (wl + wr + 2 * wc) >> 16;     // high halves: u[c-1] + 2u[c] + u[c+1] (low-half sum < 2^16: no carry)
-                    nv[e] = gx * gx + gy * gy;
-                }
+                int4 nq;
                 if (y < 0 || y >= H) {                            // uniform: neighbours outside the image never suppress (src/utils.cpp:253-304)
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) nv[e] = -1;
-                }
-                if (x_edge) {
+                    nq = make_int4(-1, -1, -1, -1);
+                } else {
+                    const int32_t* vrow = s_vu + q * kVuPitch + 4 * lane;
+                    const int4 qa = *reinterpret_cast<const int4*>(vrow);
+                    const int2 qb = *reinterpret_cast<const int2*>(vrow + 4);
+                    const int wd[6] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y};
+                    int nv[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const int x = x0 - 2 + 4 * lane + 1 + e;
-                        if (x < 0 || x >= W) nv[e] = -1;
+                        const int wl = wd[e], wc = wd[e + 1], wr = wd[e + 2];
+                        const int gx = (int)(short)(wr - wl);    // low halves: v[c+1] - v[c-1] (a borrow only disturbs the high half)
+                        const int gy = (wl + wr + 2 * wc) >> 16; // high halves: u[c-1] + 2u[c] + u[c+1] (low-half sum < 2^16: no carry)
+                        nv[e] = gx * gx + gy * gy;
                     }
-                }
-                *reinterpret_cast<int4*>(s_np + q * kNpPitch + 4 * lane) = make_int4(nv[0], nv[1], nv[2], nv[3]);
-                if (q >= 1 && q <= kSlab && y >= yb && y < ye) {   // uniform: this row is a class row of the band
-                    int mask = 0;
+                    if (x_edge) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) mask |= (nv[e] >= p.lo2) ? (1 << e) : 0;
-                    mask &= lane_mask;
-                    const unsigned vote = __ballot_sync(0xffffffffu, mask != 0);
-                    if (vote) {
-                        int base = 0;
-                        if (lane == 0) base = atomicAdd(s_count, __popc(vote));
-                        base = __shfl_sync(0xffffffffu, base, 0);
-                        if (mask) s_ent[base + __popc(vote & ((1u << lane) - 1u))] = (uint16_t)(((q - 1) << 9) | (lane << 4) | mask);
-                    }
-                    // every class word starts out as "suppressed"; phase 3b overwrites the bytes of surviving pixels
-                    const int xw = x0 + 4 * lane;
-                    if (lane < kTW / 4 && xw < W) {
-                        const long long o = (long long)frame * p.out_frame_stride + (long long)(y - p.out_row0) * W + xw;
-                        if (((W & 3) == 0) && xw + 3 < W) {
-                            *reinterpret_cast<uint32_t*>(p.cls + o) = zero_word;
-                        } else {
-                            for (int e = 0; e < 4 && xw + e < W; ++e) p.cls[o + e] = (uint8_t)p.cls_zero;
+                        for (int e = 0; e < 4; ++e) {
+                            const int x = x0 - 2 + 4 * lane + 1 + e;
+                            if (x < 0 || x >= W) nv[e] = -1;
                         }
+                    }
+                    nq = make_int4(nv[0], nv[1], nv[2], nv[3]);
+                }
+                *reinterpret_cast<int4*>(s_np + q * kNpPitch + 4 * lane) = nq;
+                if (q >= 1 && q <= kSlab && y >= yb && y < ye) {   // uniform: this row is a class row of the band
+                    const bool any = max(max(nq.x, nq.y), max(nq.z, nq.w)) >= p.lo2;
+                    const unsigned vote = __ballot_sync(0xffffffffu, any);
+                    if (any) my_ent[my_count + __popc(vote & ((1u << lane) - 1u))] = (uint16_t)(((q - 1) << 5) | lane);
+                    my_count += __popc(vote);
+                    // every class word starts out as "suppressed"; phase 3b overwrites the bytes of surviving pixels
+                    uint8_t* o = out_lane + (q - 1) * W;
+                    if (word_ok) {
+                        *reinterpret_cast<uint32_t*>(o) = zero_word;
+                    } else if (tail_ok) {
+                        for (int e = 0; e < 4 && x0 + 4 * lane + e < W; ++e) o[e] = (uint8_t)p.cls_zero;
                     }
                 }
             }
         }
-        __syncthreads();  // (C1) n-plane and candidate list complete; the zero words are ordered before phase 3b's byte stores
+        __syncthreads();  // (C1) n-plane complete; the zero words are ordered before phase 3b's byte stores
 
         // ===================== phase 3b: direction, NMS and thresholds for the candidates only =====================
         {
-            const int y_base = I_k - R - 2;
-            const int n_ent = *s_count;
-            for (int i = tid; i < n_ent; i += kThreads) {
-                const int ent = s_ent[i];
-                const int rr = ent >> 9, el = (ent >> 4) & 31, mask = ent & 15;
-                const int y = y_base + rr;
-                uint8_t* orow = p.cls + (long long)frame * p.out_frame_stride + (long long)(y - p.out_row0) * W + (x0 - 2);
+            uint8_t* out_base = p.cls + (long long)frame * p.out_frame_stride + (long long)(y_base - p.out_row0) * W + (x0 - 2);
+            for (int i = lane; i < my_count; i += 32) {
+                const int ent = my_ent[i];
+                const int rr = ent >> 5, el = ent & 31;
+                const int32_t* vrow = s_vu + (rr + 1) * kVuPitch + 4 * el;
+                const int4 qa = *reinterpret_cast<const int4*>(vrow);
+                const int2 qb = *reinterpret_cast<const int2*>(vrow + 4);
+                const int wd[6] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y};
+                const int32_t* nrow = s_np + (rr + 1) * kNpPitch + 4 * el;
+                const int4 n4 = *reinterpret_cast<const int4*>(nrow);
+                const int nc[4] = {n4.x, n4.y, n4.z, n4.w};
+                uint8_t* orow = out_base + rr * W + 4 * el + 1;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    if (!(mask & (1 << e))) continue;
+                    const int n = nc[e];
                     const int j = 4 * el + 1 + e;
-                    const int32_t* v = s_vu + (rr + 1) * kVuPitch + j;
-                    const int wl = v[-1], wc = v[0], wr = v[1];
+                    if (n < p.lo2 || j < 2 || j > kTC - 3) continue;   // j = 1 and j >= 126 are neighbour-only columns
+                    const int wl = wd[e], wc = wd[e + 1], wr = wd[e + 2];
                     const int gx = (int)(short)(wr - wl), gy = (wl + wr + 2 * wc) >> 16;
-                    const int32_t* np = s_np + (rr + 1) * kNpPitch + (j - 1);
-                    const int n = np[0];
                     const int dir = direction_code<int>(gx, gy);
                     // neighbour pair along the quantised direction (src/utils.cpp:253-304); out-of-image neighbours hold -1
                     const int off = (dir == DIR_0) ? 1 : ((dir == DIR_90) ? kNpPitch : ((dir == DIR_45) ? (1 - kNpPitch) : (1 + kNpPitch)));
-                    const int na = np[off], nb = np[-off];
-                    int cls = p.cls_zero;
+                    const int na = nrow[e + off], nb = nrow[e - off];
                     if (na < n && nb < n) {
                         // the reference compares truncated magnitudes: keep iff floor(sqrt(n_nb)) < floor(sqrt(n)) <=> n_nb < mag^2
                         const int mag = isqrt_floor(n);
                         const int m2 = mag * mag;
-                        if (na < m2 && nb < m2) cls = (n >= p.hi2) ? 255 : 1;
+                        if (na < m2 && nb < m2) orow[e] = (n >= p.hi2) ? (uint8_t)255 : (uint8_t)1;
                     }
-                    if (cls != p.cls_zero) orow[j] = (uint8_t)cls;
                 }
             }
         }

@@ -68,3 +68,15 @@ for op, n in ops.most_common(32):
 print()
 for (f, l), n in lines.most_common(nlines):
     print(f"{f}:{l:4d} {100 * n / tot:5.1f}% | {linesrc.get((f, l), '')[:120]}")
+
+# optional: --ranges file:lo-hi:name,... sums executed instructions over source line ranges
+if "--ranges" in sys.argv:
+    spec = sys.argv[sys.argv.index("--ranges") + 1]
+    px = float(sys.argv[sys.argv.index("--px") + 1]) if "--px" in sys.argv else None
+    print()
+    for item in spec.split(","):
+        f, rng, name = item.split(":")
+        lo, hi = (int(v) for v in rng.split("-"))
+        n = sum(v for (ff, l), v in lines.items() if ff == f and lo <= l <= hi)
+        extra = f"  {32 * n / px:6.1f} lane-instr/px" if px else ""
+        print(f"{name:28s} {100 * n / tot:5.1f}%{extra}")

@@ -338,55 +338,64 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
         // ===================== phase 3a: horizontal half of Sobel, magnitude^2 plane, candidate lists =====================
         // n-plane row q (0..65) <-> VU buffer row q <-> global row y_base + q - 1; it lives in the free part of the temp buffer.
         // thread = columns j = 4*lane + 1 + e (e = 0..3) of one row; n[j] is stored at word j-1 so the store is one aligned
-        // 128-bit write.  Class pixels are j = 2..125 of rows q = 1..64.  A thread with a candidate (n >= minVal^2) among its
+        // 128-bit write.  Class pixels are j = 2..125 of the class rows.  A thread with a candidate (n >= minVal^2) among its
         // four pixels appends ONE 16-bit entry {row, lane} to its WARP's list (no atomics: the count is a warp-uniform
         // register); phase 3b lets every warp work through its own list with all lanes busy.
-        const int y_base = I_k - R - 2;                           // global row of class row rr = 0
+        const int y_base = I_k - R - 2;                           // global row of class row rr = 0 (n-plane row 1)
         int my_count = 0;                                         // entries in this warp's list (uniform over the warp)
         uint16_t* my_ent = s_ent + warp * kEntPerWarp;
         {
-            // rows of the n-plane any class row of this band looks at: global rows [max(yb-1, ...), min(ye, ...)]
-            const int q_lo = max(0, yb - y_base), q_hi = min(kVuRows - 1, ye - y_base + 1);   // inclusive, uniform
-            const uint32_t zero_word = 0x01010101u * (uint32_t)p.cls_zero;
-            uint8_t* out_lane = p.cls + (long long)frame * p.out_frame_stride + (long long)(y_base - p.out_row0) * W + (x0 + 4 * lane);
-            const bool word_ok = ((W & 3) == 0) && lane < kTW / 4 && (x0 + 4 * lane + 3 < W);  // the aligned 32-bit store applies
-            const bool tail_ok = !word_ok && lane < kTW / 4 && (x0 + 4 * lane < W);            // ragged right edge: byte stores
-            for (int q = warp; q <= q_hi; q += kThreads / 32) {
-                if (q < q_lo) continue;
-                const int y = y_base + q - 1;
-                int4 nq;
-                if (y < 0 || y >= H) {                            // uniform: neighbours outside the image never suppress (src/utils.cpp:253-304)
-                    nq = make_int4(-1, -1, -1, -1);
-                } else {
-                    const int32_t* vrow = s_vu + q * kVuPitch + 4 * lane;
-                    const int4 qa = *reinterpret_cast<const int4*>(vrow);
-                    const int2 qb = *reinterpret_cast<const int2*>(vrow + 4);
-                    const int wd[6] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y};
-                    int nv[4];
+            // class rows of this slab: n-plane rows cq_lo..cq_hi (always inside the image); the rows just above and below
+            // them are neighbour-only rows and may lie outside the image
+            const int cq_lo = max(1, yb - y_base + 1), cq_hi = min(kSlab, ye - y_base);
+            auto n_of_row = [&](const int32_t* vrow) -> int4 {
+                const int4 qa = *reinterpret_cast<const int4*>(vrow);
+                const int2 qb = *reinterpret_cast<const int2*>(vrow + 4);
+                const int wd[6] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y};
+                int nv[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int wl = wd[e], wc = wd[e + 1], wr = wd[e + 2];
+                    const int gx = (int)(short)(wr - wl);    // low halves: v[c+1] - v[c-1] (a borrow only disturbs the high half)
+                    const int gy = (wl + wr + 2 * wc) >> 16; // high halves: u[c-1] + 2u[c] + u[c+1] (low-half sum < 2^16: no carry)
+                    nv[e] = gx * gx + gy * gy;
+                }
+                if (x_edge) {                                 // uniform: columns outside the image never suppress (src/utils.cpp:253-304)
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const int wl = wd[e], wc = wd[e + 1], wr = wd[e + 2];
-                        const int gx = (int)(short)(wr - wl);    // low halves: v[c+1] - v[c-1] (a borrow only disturbs the high half)
-                        const int gy = (wl + wr + 2 * wc) >> 16; // high halves: u[c-1] + 2u[c] + u[c+1] (low-half sum < 2^16: no carry)
-                        nv[e] = gx * gx + gy * gy;
+                        const int x = x0 - 2 + 4 * lane + 1 + e;
+                        if (x < 0 || x >= W) nv[e] = -1;
                     }
-                    if (x_edge) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int x = x0 - 2 + 4 * lane + 1 + e;
-                            if (x < 0 || x >= W) nv[e] = -1;
-                        }
-                    }
-                    nq = make_int4(nv[0], nv[1], nv[2], nv[3]);
                 }
-                *reinterpret_cast<int4*>(s_np + q * kNpPitch + 4 * lane) = nq;
-                if (q >= 1 && q <= kSlab && y >= yb && y < ye) {   // uniform: this row is a class row of the band
+                return make_int4(nv[0], nv[1], nv[2], nv[3]);
+            };
+            if (cq_lo <= cq_hi) {
+                // the two neighbour-only rows: warps 0 and 1
+                if (warp < 2) {
+                    const int q = warp == 0 ? cq_lo - 1 : cq_hi + 1;
+                    const int y = y_base + q - 1;
+                    int4 nq = make_int4(-1, -1, -1, -1);      // rows outside the image never suppress
+                    if (y >= 0 && y < H) nq = n_of_row(s_vu + q * kVuPitch + 4 * lane);
+                    *reinterpret_cast<int4*>(s_np + q * kNpPitch + 4 * lane) = nq;
+                }
+                const uint32_t zero_word = 0x01010101u * (uint32_t)p.cls_zero;
+                const bool word_ok = ((W & 3) == 0) && lane < kTW / 4 && (x0 + 4 * lane + 3 < W);  // the aligned 32-bit store applies
+                const bool tail_ok = !word_ok && lane < kTW / 4 && (x0 + 4 * lane < W);            // ragged right edge: byte stores
+                const unsigned lt_mask = (1u << lane) - 1u;
+                int q = cq_lo + ((warp - cq_lo) & 7);         // first class row of this warp (rows q = warp mod 8)
+                const int32_t* vrow = s_vu + q * kVuPitch + 4 * lane;
+                int32_t* nrow = s_np + q * kNpPitch + 4 * lane;
+                uint8_t* o = p.cls + (long long)frame * p.out_frame_stride + (long long)(y_base + q - 1 - p.out_row0) * W + (x0 + 4 * lane);
+                int ent = ((q - 1) << 5) | lane;
+                const long long o_step = 8LL * W;
+                for (; q <= cq_hi; q += 8, vrow += 8 * kVuPitch, nrow += 8 * kNpPitch, o += o_step, ent += 8 << 5) {
+                    const int4 nq = n_of_row(vrow);
+                    *reinterpret_cast<int4*>(nrow) = nq;
                     const bool any = max(max(nq.x, nq.y), max(nq.z, nq.w)) >= p.lo2;
                     const unsigned vote = __ballot_sync(0xffffffffu, any);
-                    if (any) my_ent[my_count + __popc(vote & ((1u << lane) - 1u))] = (uint16_t)(((q - 1) << 5) | lane);
+                    if (any) my_ent[my_count + __popc(vote & lt_mask)] = (uint16_t)ent;
                     my_count += __popc(vote);
                     // every class word starts out as "suppressed"; phase 3b overwrites the bytes of surviving pixels
-                    uint8_t* o = out_lane + (q - 1) * W;
                     if (word_ok) {
                         *reinterpret_cast<uint32_t*>(o) = zero_word;
                     } else if (tail_ok) {
@@ -399,7 +408,7 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
 
         // ===================== phase 3b: direction, NMS and thresholds for the candidates only =====================
         {
-            uint8_t* out_base = p.cls + (long long)frame * p.out_frame_stride + (long long)(y_base - p.out_row0) * W + (x0 - 2);
+            uint8_t* out_base = p.cls + (long long)frame * p.out_frame_stride + (long long)(y_base - p.out_row0) * W + (x0 - 2) + 1;
             for (int i = lane; i < my_count; i += 32) {
                 const int ent = my_ent[i];
                 const int rr = ent >> 5, el = ent & 31;
@@ -410,23 +419,36 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
                 const int32_t* nrow = s_np + (rr + 1) * kNpPitch + 4 * el;
                 const int4 n4 = *reinterpret_cast<const int4*>(nrow);
                 const int nc[4] = {n4.x, n4.y, n4.z, n4.w};
-                uint8_t* orow = out_base + rr * W + 4 * el + 1;
+                uint8_t* orow = out_base + (long long)rr * W + 4 * el;
+                // branch-free up to the local-maximum test so the four pixels' chains overlap
+                int na[4], nb[4];
+                bool pass[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int n = nc[e];
-                    const int j = 4 * el + 1 + e;
-                    if (n < p.lo2 || j < 2 || j > kTC - 3) continue;   // j = 1 and j >= 126 are neighbour-only columns
                     const int wl = wd[e], wc = wd[e + 1], wr = wd[e + 2];
                     const int gx = (int)(short)(wr - wl), gy = (wl + wr + 2 * wc) >> 16;
-                    const int dir = direction_code<int>(gx, gy);
+                    // direction_code() of canny_math.h written without early returns (same integer tests, src/utils.cpp:215-231)
+                    const int ax = abs(gx), ay = abs(gy);
+                    const int two_ax2 = 2 * ax * ax, s1 = ay + ax, d1 = ay - ax;
+                    const bool is0 = (s1 * s1 < two_ax2) || ((ax | ay) == 0);
+                    const bool is90 = (ay > ax) && (d1 * d1 > two_ax2);
+                    const bool same = (gx ^ gy) >= 0;     // only consulted when both are non-zero: (gx > 0) == (gy > 0)
                     // neighbour pair along the quantised direction (src/utils.cpp:253-304); out-of-image neighbours hold -1
-                    const int off = (dir == DIR_0) ? 1 : ((dir == DIR_90) ? kNpPitch : ((dir == DIR_45) ? (1 - kNpPitch) : (1 + kNpPitch)));
-                    const int na = nrow[e + off], nb = nrow[e - off];
-                    if (na < n && nb < n) {
+                    const int off = is0 ? 1 : (is90 ? kNpPitch : (same ? (1 - kNpPitch) : (1 + kNpPitch)));
+                    na[e] = nrow[e + off];
+                    nb[e] = nrow[e - off];
+                    const int j = 4 * el + 1 + e;
+                    pass[e] = (n >= p.lo2) && (j >= 2) && (j <= kTC - 3) && (na[e] < n) && (nb[e] < n);   // j = 1, j >= 126: neighbour-only columns
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (pass[e]) {
                         // the reference compares truncated magnitudes: keep iff floor(sqrt(n_nb)) < floor(sqrt(n)) <=> n_nb < mag^2
+                        const int n = nc[e];
                         const int mag = isqrt_floor(n);
                         const int m2 = mag * mag;
-                        if (na < m2 && nb < m2) orow[e] = (n >= p.hi2) ? (uint8_t)255 : (uint8_t)1;
+                        if (na[e] < m2 && nb[e] < m2) orow[e] = (n >= p.hi2) ? (uint8_t)255 : (uint8_t)1;
                     }
                 }
             }

@@ -37,6 +37,7 @@ cur = None
 curline = None
 first_kernel_done = False
 ops, lines, linesrc, tot = collections.Counter(), collections.Counter(), {}, 0
+samples, stot = collections.Counter(), 0
 n_func = 0
 for r in rows:
     if len(r) == 2 and r[0] == "Function Name":
@@ -47,6 +48,7 @@ for r in rows:
     if r and r[0] == "Line No":
         hdr = r
         iI = hdr.index("Instructions Executed")
+        iS = hdr.index("# Samples")
         continue
     if hdr is None or len(r) <= iI:
         continue
@@ -62,6 +64,9 @@ for r in rows:
     ops[op.split(".")[0]] += n
     lines[(cur, curline)] += n
     tot += n
+    if r[iS] not in ("-", ""):
+        samples[(cur, curline)] += int(r[iS])
+        stot += int(r[iS])
 print(f"# executed warp-instructions listed on the source page: {tot} (each SASS instruction appears once per listed launch)")
 for op, n in ops.most_common(32):
     print(f"{op:12s} {100 * n / tot:5.1f}%")
@@ -78,5 +83,6 @@ if "--ranges" in sys.argv:
         f, rng, name = item.split(":")
         lo, hi = (int(v) for v in rng.split("-"))
         n = sum(v for (ff, l), v in lines.items() if ff == f and lo <= l <= hi)
+        sm = sum(v for (ff, l), v in samples.items() if ff == f and lo <= l <= hi)
         extra = f"  {32 * n / px:6.1f} lane-instr/px" if px else ""
-        print(f"{name:28s} {100 * n / tot:5.1f}%{extra}")
+        print(f"{name:28s} instr {100 * n / tot:5.1f}%{extra}   stall samples {100 * sm / max(stot, 1):5.1f}%")

@@ -163,15 +163,31 @@ static int run_frames_device(b200_ctx* ctx, cudaStream_t st, int slot, const uin
     fp.blur = blur; fp.mag = mag; fp.ang = ang; fp.nms = nms;
     fp.w = ctx->gauss.d_w; fp.count = ctx->gauss.d_count; fp.radius = ctx->gauss.radius;
     fill_thresholds(fp, lo, hi);
-    CB_TRY(launch_front(ctx, st, fp));
+    // sparse hand-over to hysteresis (used when the lean front kernel runs): union-find slots + kept-pixel bitmap
+    fp.parent = reinterpret_cast<int32_t*>(ctx->ws_parent[slot].ptr);
+    fp.kept_count = reinterpret_cast<unsigned int*>(ctx->ws_list[slot].ptr);
+    fp.kept_list = reinterpret_cast<uint32_t*>(ctx->ws_list[slot].ptr) + 16;
+    CB_CUDA(cudaMemsetAsync(fp.kept_count, 0, sizeof(unsigned int), st));
+    bool sparse = false;
+    CB_TRY(launch_front(ctx, st, fp, &sparse));
+    const bool dense = ctx->kept_px[slot] > 0 && (long long)ctx->h_kept[slot] * 8 > ctx->kept_px[slot];   // previous launch of this slot
+    if (sparse) {
+        CB_CUDA(cudaMemcpyAsync(&ctx->h_kept[slot], fp.kept_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        ctx->kept_px[slot] = (long long)nf * px;
+    }
     HystParams hp;
     memset(&hp, 0, sizeof(hp));
     hp.cls = d_out;
+    hp.list = (sparse && !dense) ? fp.kept_list : nullptr;
+    hp.count = fp.kept_count;
     hp.parent = reinterpret_cast<int32_t*>(ctx->ws_parent[slot].ptr);
     hp.frame_stride = px; hp.rows = h; hp.width = w; hp.row0 = 0; hp.n_frames = nf;
     CB_TRY(launch_hysteresis(ctx, st, hp));
     return B200_OK;
 }
+
+// bytes of the kept-pixel list for nf frames of h x w: a counter block + one 32-bit entry per pixel (worst case: all kept)
+static size_t list_bytes(int nf, int h, int w) { return 64 + (size_t)nf * (size_t)h * (size_t)w * 4; }
 
 static int auto_chunk_frames(const b200_ctx* ctx, int h, int w, int n_frames) {
     if (ctx->chunk_frames > 0) return std::min(ctx->chunk_frames, n_frames);
@@ -218,6 +234,8 @@ int b200_ctx_create(int device, b200_ctx** out) {
         CB_CUDA(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
     }
     CB_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_kept), 4 * sizeof(unsigned int)));
+    memset(c->h_kept, 0, 4 * sizeof(unsigned int));
     *out = c;
     return B200_OK;
 }
@@ -227,9 +245,10 @@ int b200_ctx_destroy(b200_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     auto rel = [](Workspace& w, bool pinned) { if (w.ptr) { if (pinned) cudaFreeHost(w.ptr); else cudaFree(w.ptr); w.ptr = nullptr; w.bytes = 0; } };
-    for (int i = 0; i < 3; ++i) { rel(c->ws_parent[i], false); rel(c->dev_in[i], false); rel(c->dev_out[i], false); }
-    rel(c->ws_planes, false); rel(c->ws_misc, false); rel(c->ws_band_parent, false);
+    for (int i = 0; i < 3; ++i) { rel(c->ws_parent[i], false); rel(c->ws_list[i], false); rel(c->dev_in[i], false); rel(c->dev_out[i], false); }
+    rel(c->ws_planes, false); rel(c->ws_misc, false); rel(c->ws_band_parent, false); rel(c->ws_band_list, false); rel(c->ws_band_aux, false);
     if (c->gauss.d_w) cudaFree(c->gauss.d_w);
+    if (c->h_kept) cudaFreeHost(c->h_kept);
     for (int i = 0; i < 3; ++i) { if (c->side[i]) cudaStreamDestroy(c->side[i]); if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -390,6 +409,7 @@ int b200_canny_steps(b200_ctx* ctx, const uint8_t* img, float sigma, int lo, int
     Planes pl;
     CB_TRY(get_planes(ctx, px, pl));
     CB_TRY(ensure_ws(ctx->ws_parent[0], (size_t)px * 4));
+    CB_TRY(ensure_ws(ctx->ws_list[0], list_bytes(1, h, w)));
     cudaStream_t st = ctx->stream;
     CB_CUDA(cudaMemcpyAsync(pl.in, img, (size_t)px, cudaMemcpyHostToDevice, st));
     CB_TRY(run_frames_device(ctx, st, 0, pl.in, pl.cls, 1, h, w, lo, hi, blur ? pl.p16[0] : nullptr,
@@ -419,7 +439,10 @@ int b200_canny_batch_device(b200_ctx* ctx, const uint8_t* d_frames, int n_frames
     const int chunk = auto_chunk_frames(ctx, h, w, n_frames);
     const int n_chunks = (n_frames + chunk - 1) / chunk;
     const int n_slots = n_chunks >= 2 ? 2 : 1;
-    for (int s = 0; s < n_slots; ++s) CB_TRY(ensure_ws(ctx->ws_parent[s], (size_t)px * 4 * (size_t)chunk));
+    for (int s = 0; s < n_slots; ++s) {
+        CB_TRY(ensure_ws(ctx->ws_parent[s], (size_t)px * 4 * (size_t)chunk));
+        CB_TRY(ensure_ws(ctx->ws_list[s], list_bytes(chunk, h, w)));
+    }
     if (n_slots == 1) {
         CB_TRY(run_frames_device(ctx, ctx->stream, 0, d_frames, d_edges, n_frames, h, w, lo, hi, nullptr, nullptr, nullptr, nullptr));
         return B200_OK;
@@ -454,6 +477,7 @@ int b200_canny_batch_host(b200_ctx* ctx, const uint8_t* frames, int n_frames, in
     const int n_slots = std::min(3, n_chunks);
     for (int s = 0; s < n_slots; ++s) {
         CB_TRY(ensure_ws(ctx->ws_parent[s], (size_t)px * 4 * (size_t)chunk));
+        CB_TRY(ensure_ws(ctx->ws_list[s], list_bytes(chunk, h, w)));
         CB_TRY(ensure_ws(ctx->dev_in[s], (size_t)px * (size_t)chunk));
         CB_TRY(ensure_ws(ctx->dev_out[s], (size_t)px * (size_t)chunk));
     }
@@ -487,6 +511,7 @@ int b200_profile_stages_device(b200_ctx* ctx, const uint8_t* d_frames, int n_fra
     const long long px = (long long)h * w;
     const int chunk = auto_chunk_frames(ctx, h, w, n_frames);
     CB_TRY(ensure_ws(ctx->ws_parent[0], (size_t)px * 4 * (size_t)chunk));
+    CB_TRY(ensure_ws(ctx->ws_list[0], list_bytes(chunk, h, w)));
     CB_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->prof.recs.clear();
     ctx->prof.on = true;

@@ -145,6 +145,7 @@ int b200_band_front(b200_ctx* ctx, const uint8_t* d_rows, int halo_above, int ha
     }
     const long long px = (long long)band_rows * width;
     CB_TRY(ensure_ws(ctx->ws_band_parent, (size_t)px * 4));
+    CB_TRY(ensure_ws(ctx->ws_band_list, 64 + (size_t)px * 4));
     cudaStream_t st = ctx->stream;
     FrontParams fp;
     memset(&fp, 0, sizeof(fp));
@@ -162,9 +163,23 @@ int b200_band_front(b200_ctx* ctx, const uint8_t* d_rows, int halo_above, int ha
         fp.lo = lo; fp.hi = hi; fp.lo2 = sq(lo); fp.hi2 = sq(hi);
         fp.cls_zero = (0 >= lo) ? ((0 >= hi) ? 255 : 1) : 0;
     }
-    CB_TRY(launch_front(ctx, st, fp));
+    fp.parent = reinterpret_cast<int32_t*>(ctx->ws_band_parent.ptr);
+    fp.kept_count = reinterpret_cast<unsigned int*>(ctx->ws_band_list.ptr);
+    fp.kept_list = reinterpret_cast<uint32_t*>(ctx->ws_band_list.ptr) + 16;
+    CB_CUDA(cudaMemsetAsync(fp.kept_count, 0, sizeof(unsigned int), st));
+    bool sparse = false;
+    CB_TRY(launch_front(ctx, st, fp, &sparse));
+    const bool dense = ctx->kept_px[3] > 0 && (long long)ctx->h_kept[3] * 8 > ctx->kept_px[3];   // previous band on this context
+    if (sparse) {
+        CB_CUDA(cudaMemcpyAsync(&ctx->h_kept[3], fp.kept_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        ctx->kept_px[3] = px;
+    }
+    sparse = sparse && !dense;
+    ctx->band_sparse = sparse;
     HystParams hp;
     memset(&hp, 0, sizeof(hp));
+    hp.list = sparse ? fp.kept_list : nullptr;
+    hp.count = fp.kept_count;
     hp.cls = d_edges; hp.parent = reinterpret_cast<int32_t*>(ctx->ws_band_parent.ptr);
     hp.frame_stride = px; hp.rows = band_rows; hp.width = width; hp.row0 = row0; hp.n_frames = 1;
     CB_TRY(launch_ccl_label(ctx, st, hp));
@@ -236,6 +251,8 @@ int b200_band_finalize(b200_ctx* ctx, const b200_band_record* d_all, int n_bands
     HystParams hp;
     memset(&hp, 0, sizeof(hp));
     hp.cls = d_edges; hp.parent = parent;
+    hp.list = ctx->band_sparse ? reinterpret_cast<const uint32_t*>(ctx->ws_band_list.ptr) + 16 : nullptr;
+    hp.count = reinterpret_cast<const unsigned int*>(ctx->ws_band_list.ptr);
     hp.frame_stride = (long long)band_rows * width; hp.rows = band_rows; hp.width = width; hp.row0 = ctx->band_row0; hp.n_frames = 1;
     CB_TRY(launch_ccl_resolve(ctx, st, hp));
     return B200_OK;

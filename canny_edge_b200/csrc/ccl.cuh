@@ -58,5 +58,30 @@ __device__ __forceinline__ void g_union(int32_t* parent, int a, int b) {
     }
 }
 
+// find with path halving (the sparse kernels: chains along a long edge would otherwise be walked again and again).
+// Values only ever move towards the root, so the racy plain store is benign; negative values are terminal and never stored.
+__device__ __forceinline__ int g_find_halve(int32_t* parent, int x) {
+    while (x >= 0) {
+        const int p = __ldcg(parent + x);
+        if (p == x || p < 0) return p < 0 ? p : x;
+        const int gp = __ldcg(parent + p);
+        if (gp == p) return p;
+        if (gp < 0) return gp;
+        parent[x] = gp;
+        x = gp;
+    }
+    return x;
+}
+__device__ __forceinline__ void g_union_halve(int32_t* parent, int a, int b) {
+    while (true) {
+        a = g_find_halve(parent, a);
+        b = g_find_halve(parent, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }  // a > b >= SUPER; a is a real slot
+        const int old = atomicMin(parent + a, b);
+        if (old == a) return;
+        a = old;
+    }
+}
 
 }  // namespace cb

@@ -546,8 +546,9 @@ static int launch_front_v1(b200_ctx* ctx, cudaStream_t st, const FrontParams& p_
 
 // Dispatcher: the lean kernel (front2.cu) for the hot configuration — compile-time radius, no spill planes,
 // ordinary sigma; front_kernel above for everything else.  B200_CANNY_FRONT=1 forces the first kernel (A/B runs).
-int launch_front(b200_ctx* ctx, cudaStream_t st, const FrontParams& p_in) {
+int launch_front(b200_ctx* ctx, cudaStream_t st, const FrontParams& p_in, bool* sparse_out) {
     FrontParams p = p_in;
+    if (sparse_out) *sparse_out = false;
     p.ieee_div = ctx->gauss.tiny ? 1 : 0;
     const int radius = p.radius;
     if (radius < 1 || radius > B200_MAX_RADIUS) {
@@ -556,7 +557,15 @@ int launch_front(b200_ctx* ctx, cudaStream_t st, const FrontParams& p_in) {
     }
     static const bool force_v1 = [] { const char* e = getenv("B200_CANNY_FRONT"); return e && e[0] == '1'; }();
     const bool spill = p.blur || p.mag || p.ang || p.nms;
-    if (!force_v1 && !spill && !ctx->gauss.tiny && front2_supports(radius)) return launch_front2(ctx, st, p);
+    if (!force_v1 && !spill && !ctx->gauss.tiny && front2_supports(radius)) {
+        // the sparse hand-over lists KEPT pixels; with minVal <= 0 suppressed pixels are candidates too (src/utils.cpp:328), so the
+        // whole-plane labelling has to run
+        const bool sparse = p.parent != nullptr && p.kept_list != nullptr && p.kept_count != nullptr && p.cls_zero == 0 &&
+                            (long long)p.n_frames * p.out_frame_stride < (1LL << 31);
+        if (!sparse) { p.parent = nullptr; p.kept_list = nullptr; p.kept_count = nullptr; }
+        if (sparse_out) *sparse_out = sparse;
+        return launch_front2(ctx, st, p);
+    }
     return launch_front_v1(ctx, st, p);
 }
 

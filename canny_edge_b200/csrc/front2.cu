@@ -54,7 +54,7 @@ constexpr int kEntPerWarp = (kSlab / 8) * 32;  // candidate list of one warp: at
 constexpr int kMaxEnt = 8 * kEntPerWarp;
 
 struct SmemLayout {
-    int in_off, temp_off, vu_off, ent_off, tab_off, w_off, bar_off, total;
+    int in_off, temp_off, vu_off, ent_off, bits_off, tab_off, w_off, bar_off, total;
 };
 __host__ __device__ constexpr SmemLayout smem_layout(int radius) {
     SmemLayout L{};
@@ -64,6 +64,7 @@ __host__ __device__ constexpr SmemLayout smem_layout(int radius) {
     L.temp_off = o; o += temp_rows_for(radius) * kTempPitch * 4;
     L.vu_off = o;   o += kVuRows * kVuPitch * 4;
     L.ent_off = o;  o += kMaxEnt * 2;
+    L.bits_off = o; o += kSlab * 4 * 4;                        // kept-pixel bitmap of the slab's class rows: 4 words per row
     L.tab_off = o;  o += 2 * (radius + 1) * (radius + 1) * 4;  // count table, reciprocal table
     L.w_off = o;    o += (2 * radius + 1) * 4;
     o = (o + 15) & ~15;
@@ -107,6 +108,8 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
     float* s_w = reinterpret_cast<float*>(smem + L.w_off);
     const uint32_t bar0 = smem_u32(smem + L.bar_off);
     uint16_t* s_ent = reinterpret_cast<uint16_t*>(smem + L.ent_off);
+    uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem + L.bits_off);
+    const bool sparse = p.kept_list != nullptr;                  // uniform: also fill parent[] and the kept-pixel list
     int32_t* s_np = reinterpret_cast<int32_t*>(s_temp + T0 * kTempPitch);   // n-plane: the temp rows phase 1 refills next slab
 
     const int tid = threadIdx.x;
@@ -130,6 +133,7 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
         s_rcp[i] = p.count[(R + 1) * (R + 1) + i];
     }
     for (int i = tid; i < 2 * R + 1; i += kThreads) s_w[i] = p.w[i];
+    s_bits[tid] = 0;                                             // kThreads == kSlab * 4 words
     if (USE_TMA && tid == 0) {
         mbar_init(bar0, 1);
         mbar_init(bar0 + 8, 1);
@@ -176,6 +180,22 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
         issue_slab(0);
         if (n_slabs > 1) issue_slab(1);
     }
+
+    // kept-pixel list entries of the previous slab, waiting for their reservation (see the end of the loop body)
+    uint32_t pend_bits = 0;
+    unsigned int pend_base = 0;
+    int pend_off = 0, pend_g0 = 0;
+    auto flush_pending = [&]() {
+        const unsigned int base = __shfl_sync(0xffffffffu, pend_base, 0);
+        uint32_t* dst = p.kept_list + base + pend_off;
+        uint32_t m = pend_bits;
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            *dst++ = (uint32_t)(pend_g0 + b);
+        }
+        pend_bits = 0;
+    };
 
     for (int k = 0; k < n_slabs; ++k) {
         const int I_k = in_y0 + k * kSlab;  // global row of this slab's first input line
@@ -256,6 +276,7 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
                     }
                 });
         }
+        if (sparse) flush_pending();
         __syncthreads();  // (A) this slab's temp lines are complete; staged buffer k&1 is free again
         if (USE_TMA && k + 2 < n_slabs) issue_slab(k + 2);
 
@@ -408,7 +429,10 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
 
         // ===================== phase 3b: direction, NMS and thresholds for the candidates only =====================
         {
-            uint8_t* out_base = p.cls + (long long)frame * p.out_frame_stride + (long long)(y_base - p.out_row0) * W + (x0 - 2) + 1;
+            const long long out_off = (long long)frame * p.out_frame_stride + (long long)(y_base - p.out_row0) * W + (x0 - 2) + 1;
+            uint8_t* out_base = p.cls + out_off;
+            int32_t* par_base = p.parent + out_off;                           // only dereferenced when `sparse`
+            const int idx_base = (int)out_off;                                // launch-relative pixel index of (class row 0, column j = 1)
             for (int i = lane; i < my_count; i += 32) {
                 const int ent = my_ent[i];
                 const int rr = ent >> 5, el = ent & 31;
@@ -448,16 +472,49 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
                         const int n = nc[e];
                         const int mag = isqrt_floor(n);
                         const int m2 = mag * mag;
-                        if (na[e] < m2 && nb[e] < m2) orow[e] = (n >= p.hi2) ? (uint8_t)255 : (uint8_t)1;
+                        if (na[e] < m2 && nb[e] < m2) {
+                            const bool strong = n >= p.hi2;
+                            orow[e] = strong ? (uint8_t)255 : (uint8_t)1;
+                            if (sparse) {
+                                // hand-over to the sparse hysteresis kernels: the pixel's union-find slot (itself, or the virtual
+                                // root SUPER = -1 of every strong component) and its bit in the slab's kept-pixel bitmap, from which
+                                // the list entries are made once the slab is finished
+                                const int rel = rr * W + 4 * el + e;
+                                par_base[rel] = strong ? -1 : idx_base + rel;
+                                const int col = 4 * el + e - 1;               // class column within the strip: j - 2
+                                atomicOr(&s_bits[rr * 4 + (col >> 5)], 1u << (col & 31));
+                            }
+                        }
                     }
                 }
             }
         }
-        __syncthreads();  // (C) VU, n-plane and list reads done
+        __syncthreads();  // (C) VU, n-plane and list reads done; the slab's kept-pixel bitmap is complete
+        if (sparse) {
+            // append this slab's kept pixels to the launch-wide list: every warp counts the bits of its 32 bitmap words and reserves
+            // room with ONE global atomicAdd.  The atomic's round trip is hidden behind the next slab's row pass: the entries are
+            // written by flush_pending() after it (and once more after the last slab).
+            pend_bits = s_bits[tid];
+            s_bits[tid] = 0;
+            const int cnt = __popc(pend_bits);
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            pend_base = 0;
+            if (total && lane == 0) pend_base = atomicAdd(p.kept_count, (unsigned int)total);
+            pend_off = incl - cnt;
+            // word tid <-> class row rr = tid >> 2, columns 32*(tid & 3) .. of the strip
+            pend_g0 = (int)((long long)frame * p.out_frame_stride + (long long)(y_base + (tid >> 2) - p.out_row0) * W + x0 + 32 * (tid & 3));
+        }
         // VU rows 64,65 (blurred-row neighbours of the next slab's first class rows) -> rows 0,1
         if (k + 1 < n_slabs) s_vu[(tid >> 7) * kVuPitch + (tid & 127)] = s_vu[(kSlab + (tid >> 7)) * kVuPitch + (tid & 127)];
         // the next iteration's barrier (A) orders this copy before phase 2 rewrites rows 2..65 and phase 3 reads rows 0,1
     }
+    if (sparse) flush_pending();
 }
 
 }  // namespace f2

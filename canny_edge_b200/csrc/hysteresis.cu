@@ -249,8 +249,94 @@ ccl_final_kernel(const HystParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// sparse variants: driven by the kept-pixel list front2.cu writes (work ~ number of kept pixels, not pixels)
+// ---------------------------------------------------------------------------------------------
+// front2 has already initialised parent[] for every kept pixel (its own launch-relative index; SUPER for strong pixels).  One
+// thread per kept pixel: it looks at its "forward" neighbours E, S (or SW / SE when S is not kept: with S kept the two diagonals
+// reach the pixel through S's own E links), so every undirected neighbour pair is visited exactly once, from its earlier endpoint
+// in raster order.  Two strong pixels already share the root SUPER; a strong and a weak one only need the weak one's component
+// hung under SUPER; only weak-weak pairs are real unions.  The pair (0,1)-(1,0) of the GLOBAL image is skipped (see the file header).
+__device__ __forceinline__ void sparse_link(int32_t* parent, int a, int ca, int b, int cb) {
+    if (ca == 255) {
+        if (cb != 255) g_union_halve(parent, b, kSuper);
+    } else if (cb == 255) {
+        g_union_halve(parent, a, kSuper);
+    } else {
+        g_union_halve(parent, a, b);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+ccl_sparse_link_kernel(const HystParams p) {
+    const unsigned int n = *p.count;
+    const int W = p.width, Hh = p.rows;
+    const unsigned int fs = (unsigned int)p.frame_stride;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned int g = p.list[i];
+        const unsigned int rel = g % fs;
+        const int y = (int)(rel / (unsigned int)W), x = (int)(rel - (unsigned int)y * (unsigned int)W);
+        const uint8_t* c = p.cls + g;
+        const int ca = c[0];
+        if (x + 1 < W) {
+            const int ce = c[1];
+            if (ce) sparse_link(p.parent, (int)g, ca, (int)g + 1, ce);
+        }
+        if (y + 1 < Hh) {
+            const int cs = c[W];
+            if (cs) {
+                sparse_link(p.parent, (int)g, ca, (int)g + W, cs);
+            } else {
+                const bool quirk = (p.row0 + y == 0) && (x == 1);   // (0,1) -> its SW neighbour (1,0)
+                if (x > 0 && !quirk) {
+                    const int cw = c[W - 1];
+                    if (cw) sparse_link(p.parent, (int)g, ca, (int)g + W - 1, cw);
+                }
+                if (x + 1 < W) {
+                    const int cx = c[W + 1];
+                    if (cx) sparse_link(p.parent, (int)g, ca, (int)g + W + 1, cx);
+                }
+            }
+        }
+    }
+}
+
+// every kept WEAK pixel chases its root: 255 when the component hangs under SUPER (or is the target of the one-way link), else 0
+__global__ void __launch_bounds__(256)
+ccl_sparse_resolve_kernel(const HystParams p) {
+    const unsigned int n = *p.count;
+    const int W = p.width, Hh = p.rows;
+    const unsigned int fs = (unsigned int)p.frame_stride;
+    const bool q_possible = (p.row0 == 0 && Hh >= 2 && W >= 2);
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned int g = p.list[i];
+        if (p.cls[g] != 1) continue;
+        const int root = g_find_halve(p.parent, (int)g);
+        bool on = (root == kSuper);
+        if (!on && q_possible) {
+            // the one-way link (0,1) -> (1,0) of the global image: if (0,1)'s component is strong, (1,0)'s becomes strong.  Reading
+            // the two class bytes while this kernel rewrites weak ones is benign: a byte only ever turns 0 when its component is
+            // neither strong nor the link's target, in which case the link does not apply anyway.
+            const unsigned int f0 = g - g % fs;
+            if (p.cls[f0 + 1] != 0 && p.cls[f0 + W] != 0 && g_find_halve(p.parent, (int)f0 + 1) == kSuper)
+                on = (root == g_find_halve(p.parent, (int)f0 + W));
+        }
+        p.cls[g] = on ? 255 : 0;
+    }
+}
+
+// the list length lives on the device: a fixed grid (every SM full once) strides over it
+static int sparse_grid(const b200_ctx* ctx) { return 8 * (ctx->sm_count > 0 ? ctx->sm_count : 148); }
+
 int launch_ccl_label(b200_ctx* ctx, cudaStream_t st, const HystParams& p_in) {
     HystParams p = p_in;
+    if (p.list) {
+        ProfScope ps(ctx, st, 1);
+        ccl_sparse_link_kernel<<<sparse_grid(ctx), 256, 0, st>>>(p);
+        CB_CUDA(cudaGetLastError());
+        ctx->launches++;
+        return B200_OK;
+    }
     p.tiles_x = (p.width + kTile - 1) / kTile;
     p.tiles_y = (p.rows + kTile - 1) / kTile;
     {
@@ -277,6 +363,13 @@ int launch_ccl_label(b200_ctx* ctx, cudaStream_t st, const HystParams& p_in) {
 
 int launch_ccl_resolve(b200_ctx* ctx, cudaStream_t st, const HystParams& p_in) {
     HystParams p = p_in;
+    if (p.list) {
+        ProfScope ps(ctx, st, 3);
+        ccl_sparse_resolve_kernel<<<sparse_grid(ctx), 256, 0, st>>>(p);
+        CB_CUDA(cudaGetLastError());
+        ctx->launches++;
+        return B200_OK;
+    }
     p.tiles_x = (p.width + kTile - 1) / kTile;
     p.tiles_y = (p.rows + kTile - 1) / kTile;
     const long long n16 = ((long long)p.rows * p.width + 15) / 16;

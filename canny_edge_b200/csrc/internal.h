@@ -70,6 +70,11 @@ struct FrontParams {
     int cls_zero;           // class of a suppressed pixel (value 0): nonzero only when lo <= 0
     int ieee_div;           // 1: weights so small that sums can fall below 2^-100 -> use IEEE division instead of div_exact
     int tiles_x, tiles_y;
+    // sparse hand-over to the hysteresis kernels (front2.cu only; both null -> not produced):
+    int32_t* parent;        // union-find slots, indexed like cls: every kept pixel is initialised (its own launch-relative index
+                            // frame*out_frame_stride + pixel, or SUPER when strong)
+    uint32_t* kept_list;    // launch-relative indices of all kept pixels, in no particular order
+    unsigned int* kept_count;  // number of entries (zeroed by the host before the launch)
 };
 
 // ---- parameters of the hysteresis (connected components) kernels ---------------------------------
@@ -81,6 +86,8 @@ struct HystParams {
     int row0;              // global row of plane row 0 (the missing-link quirk lives at global (1,0)->(0,1))
     int n_frames;
     int tiles_x, tiles_y;
+    const uint32_t* list;        // kept-pixel list written by front2 (null -> tile-based labelling over the whole plane);
+    const unsigned int* count;   // the list-driven kernels keep LAUNCH-relative indices (frame*frame_stride + pixel) in parent[]
 };
 
 // ---- the context ------------------------------------------------------------------------------
@@ -110,6 +117,8 @@ struct b200_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     cb::GaussTables gauss;
     cb::Workspace ws_parent[3];   // int32 union-find slots for one chunk, per pipeline slot
+    cb::Workspace ws_list[3];     // kept-pixel lists for one chunk ([0..15] = counter block, entries from word 16), per pipeline slot
+    cb::Workspace ws_band_list;   // kept-pixel list of the resident band
     cb::Workspace ws_planes;      // stage-API scratch planes
     cb::Workspace ws_misc;
     cb::Workspace dev_in[3], dev_out[3];  // device staging for the batch_host pipeline
@@ -121,6 +130,12 @@ struct b200_ctx {
     // band state (row-band sharding)
     int band_rows = 0, band_width = 0, band_row0 = 0;
     uint8_t* band_cls = nullptr;          // class map of the resident band (caller's d_edges)
+    bool band_sparse = false;             // the resident band's labels were built from the kept-pixel list
+    // kept-pixel count of the last launch of each pipeline slot, copied back asynchronously (pinned host memory, never waited
+    // for): when the previous launch kept more than 1/8 of its pixels the next one uses the tile-based labelling, whose shared-
+    // memory unions win on dense maps.  Both give identical results; a stale value only costs speed.
+    unsigned int* h_kept = nullptr;       // [4]: slots 0..2 + the band
+    long long kept_px[4] = {0, 0, 0, 0};
 };
 
 namespace cb {
@@ -145,7 +160,8 @@ void host_gaussian_kernel(float sigma, std::vector<float>& w);
 int host_window(float sigma);
 
 // front.cu
-int launch_front(b200_ctx* ctx, cudaStream_t st, const FrontParams& p);
+// *sparse_out (optional) tells whether the kernel that ran filled p.parent / p.kept_list
+int launch_front(b200_ctx* ctx, cudaStream_t st, const FrontParams& p, bool* sparse_out = nullptr);
 int make_input_tensor_map(const FrontParams& p, int box_cols, int box_rows, CUtensorMap_st* tmap, bool* use_tma);
 // front2.cu
 bool front2_supports(int radius);

@@ -409,18 +409,30 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
                 uint8_t* o = p.cls + (long long)frame * p.out_frame_stride + (long long)(y_base + q - 1 - p.out_row0) * W + (x0 + 4 * lane);
                 int ent = ((q - 1) << 5) | lane;
                 const long long o_step = 8LL * W;
-                for (; q <= cq_hi; q += 8, vrow += 8 * kVuPitch, nrow += 8 * kNpPitch, o += o_step, ent += 8 << 5) {
-                    const int4 nq = n_of_row(vrow);
-                    *reinterpret_cast<int4*>(nrow) = nq;
+                // two copies of the loop so the store form is decided once, not per row: the aligned 32-bit store (every strip of
+                // an image whose width is a multiple of 4, except a ragged last strip) or byte stores
+                auto class_row = [&](const int32_t* vr, int32_t* nr, int e16) {
+                    const int4 nq = n_of_row(vr);
+                    *reinterpret_cast<int4*>(nr) = nq;
                     const bool any = max(max(nq.x, nq.y), max(nq.z, nq.w)) >= p.lo2;
                     const unsigned vote = __ballot_sync(0xffffffffu, any);
-                    if (any) my_ent[my_count + __popc(vote & lt_mask)] = (uint16_t)ent;
+                    if (any) my_ent[my_count + __popc(vote & lt_mask)] = (uint16_t)e16;
                     my_count += __popc(vote);
-                    // every class word starts out as "suppressed"; phase 3b overwrites the bytes of surviving pixels
-                    if (word_ok) {
-                        *reinterpret_cast<uint32_t*>(o) = zero_word;
-                    } else if (tail_ok) {
-                        for (int e = 0; e < 4 && x0 + 4 * lane + e < W; ++e) o[e] = (uint8_t)p.cls_zero;
+                };
+                // every class word starts out as "suppressed"; phase 3b overwrites the bytes of surviving pixels
+                if (__all_sync(0xffffffffu, word_ok || lane >= kTW / 4)) {
+                    for (; q <= cq_hi; q += 8, vrow += 8 * kVuPitch, nrow += 8 * kNpPitch, o += o_step, ent += 8 << 5) {
+                        class_row(vrow, nrow, ent);
+                        if (lane < kTW / 4) *reinterpret_cast<uint32_t*>(o) = zero_word;
+                    }
+                } else {
+                    for (; q <= cq_hi; q += 8, vrow += 8 * kVuPitch, nrow += 8 * kNpPitch, o += o_step, ent += 8 << 5) {
+                        class_row(vrow, nrow, ent);
+                        if (word_ok) {
+                            *reinterpret_cast<uint32_t*>(o) = zero_word;
+                        } else if (tail_ok) {
+                            for (int e = 0; e < 4 && x0 + 4 * lane + e < W; ++e) o[e] = (uint8_t)p.cls_zero;
+                        }
                     }
                 }
             }
@@ -452,12 +464,18 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
                     const int n = nc[e];
                     const int wl = wd[e], wc = wd[e + 1], wr = wd[e + 2];
                     const int gx = (int)(short)(wr - wl), gy = (wl + wr + 2 * wc) >> 16;
-                    // direction_code() of canny_math.h written without early returns (same integer tests, src/utils.cpp:215-231)
-                    const int ax = abs(gx), ay = abs(gy);
-                    const int two_ax2 = 2 * ax * ax, s1 = ay + ax, d1 = ay - ax;
-                    const bool is0 = (s1 * s1 < two_ax2) || ((ax | ay) == 0);
-                    const bool is90 = (ay > ax) && (d1 * d1 > two_ax2);
-                    const bool same = (gx ^ gy) >= 0;     // only consulted when both are non-zero: (gx > 0) == (gy > 0)
+                    // direction_code() of canny_math.h in product form (same integer tests as src/utils.cpp:215-231's bins):
+                    //   0   <=> (ay+ax)^2 < 2ax^2           <=> ax^2 - ay^2 > 2 ax ay
+                    //   90  <=> ay > ax and (ay-ax)^2 > 2ax^2 <=> ay^2 - ax^2 > 2 ax ay
+                    //   else a diagonal: 45 when gx and gy have the same sign (gx*gy > 0; both are non-zero there).
+                    // gx = gy = 0 lands on "45" instead of 0, which cannot change the class: such a pixel is a candidate only when
+                    // minVal <= 0, and then kept and suppressed pixels get the same class (see fill_thresholds()).
+                    const int pxy = gx * gy;
+                    const int dd = 2 * gx * gx - n;           // ax^2 - ay^2  (n = ax^2 + ay^2)
+                    const int p2 = 2 * abs(pxy);
+                    const bool is0 = dd > p2;
+                    const bool is90 = -dd > p2;
+                    const bool same = pxy >= 0;
                     // neighbour pair along the quantised direction (src/utils.cpp:253-304); out-of-image neighbours hold -1
                     const int off = is0 ? 1 : (is90 ? kNpPitch : (same ? (1 - kNpPitch) : (1 + kNpPitch)));
                     na[e] = nrow[e + off];

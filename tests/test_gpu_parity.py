@@ -278,3 +278,39 @@ def test_idempotent_and_monotone(gpu_ctx):
     assert set(np.unique(e1).tolist()) <= {0, 255}
     assert not ((e2 == 255) & (e1 == 0)).any()
     assert_same("deterministic", cb.cuda_canny(img, 1.4, 20, 60, ctx=gpu_ctx), e1)
+
+
+def test_dense_and_sparse_hysteresis_paths_agree(oracle):
+    """The fused path picks its labelling kernels from the PREVIOUS launch's kept-pixel density (list-driven kernels for sparse
+    maps, tile-based ones above 1/8 kept): run dense and sparse frames alternately on ONE context so both families and both
+    switches are exercised; every result must match the oracle."""
+    ctx = cb.Context(0)
+    try:
+        noise = cb.synth_host(2, 270, 480, kind=1, seed=21)
+        shapes = cb.synth_host(2, 270, 480, kind=0, seed=22)
+        seq = [noise, noise, noise, shapes, shapes, noise, shapes]
+        for i, frames in enumerate(seq):
+            out = cb.canny_batch_host(frames, 1.4, 20, 60, ctx=ctx)
+            for f in range(frames.shape[0]):
+                assert_same(f"step {i} frame {f}", out[f].astype(np.int16), oracle.canny(frames[f], 1.4, 20, 60))
+        # single-frame API on the same context (slot 0 history is dense or sparse depending on the last batch)
+        for img in (noise[0], shapes[1], noise[1]):
+            assert_same("single", cb.cuda_canny(img, 1.4, 20, 60, ctx=ctx), oracle.canny(img, 1.4, 20, 60))
+    finally:
+        ctx.close()
+
+
+def test_sparse_hysteresis_long_chains(gpu_ctx, oracle):
+    """Long weak chains with a single seed (the list-driven union-find walks them with path halving), incl. the (1,0)->(0,1) quirk
+    pixel pair at the image corner."""
+    h, w = 600, 500
+    img = np.full((h, w), 90, np.uint8)
+    for k in range(0, 200, 8):                                   # a square spiral, 3 px wide, faint
+        img[k:k + 3, k:w - k] = 99; img[k:h - k, w - k - 3:w - k] = 99; img[h - k - 3:h - k, k:w - k] = 99; img[k + 8:h - k, k:k + 3] = 99
+    img[1:3, 0:6] = 230                                           # one bright blob at the corner
+    assert_same("spiral", cb.cuda_canny(img, 1.0, 3, 60, ctx=gpu_ctx), oracle.canny(img, 1.0, 3, 60))
+    rng = np.random.default_rng(4)
+    for _ in range(10):                                           # random corner patterns around the quirk pixels
+        im = np.full((64, 64), 100, np.uint8)
+        im[:4, :4] = rng.integers(0, 256, (4, 4))
+        assert_same("corner", cb.cuda_canny(im, 0.5, 5, 120, ctx=gpu_ctx), oracle.canny(im, 0.5, 5, 120))

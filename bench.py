@@ -247,7 +247,9 @@ def run_b200(a, rank, world, local_rank):
     # ---- roofline of the dominant kernel, measured live with CUDA events on the launching stream ----
     ms5, cnt5 = (C.c_float * 5)(), (C.c_int * 5)()
     check(lib.b200_profile_stages_device(ctx.handle, d_in.data_ptr(), n, h, w, C.c_float(SIGMA), LO, HI, d_out.data_ptr(), ms5, cnt5))
-    names = ["front", "ccl_local", "ccl_merge", "ccl_final", "other"]
+    # category 1 = labelling (list-driven link kernel, or tile-local union-find on dense maps), 2 = tile-border merge (dense maps
+    # only), 3 = resolve (weak pixels -> 0 / 255)
+    names = ["front", "hyst_label", "hyst_merge", "hyst_resolve", "other"]
     total_k = sum(ms5)
     stage = {names[i]: {"ms": round(ms5[i], 3), "launches": cnt5[i], "share": round(ms5[i] / total_k, 4) if total_k else None}
              for i in range(4)}
@@ -255,10 +257,11 @@ def run_b200(a, rank, world, local_rank):
     front_launches = max(cnt5[0], 1)
     bytes_per_launch = ALG_BYTES_PER_PX * px / front_launches
     achieved = bytes_per_launch / (ms5[0] / front_launches * 1e-3) / 1e9 if ms5[0] > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "front_kernel (blur+Sobel+NMS+classify)", "achieved": round(achieved, 2), "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "front2_kernel (blur + Sobel + NMS + thresholds, u8 in -> u8 class map)", "achieved": round(achieved, 2), "peak": peak,
                 "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_px": ALG_BYTES_PER_PX, "launch_ms": round(ms5[0] / front_launches, 4),
-                "note": "issue-bound, not HBM-bound: see DESIGN.md (bit-exact float blur costs ~50 FP32 instr/px)",
+                "note": "issue-bound, not HBM-bound: the reference's rounding order costs ~47 un-fusable FP32 lane-instructions per pixel "
+                        "for the 11-tap separable blur alone (DESIGN.md 4.1, profiles/)",
                 "whole_pipeline_frac": round(value / world * 1e6 * ALG_BYTES_PER_PX / 1e9 / peak, 5), "stages": stage}
     prof = ROOT / "profiles" / "traffic.json"
     if prof.exists():

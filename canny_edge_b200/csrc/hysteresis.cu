@@ -277,26 +277,21 @@ ccl_sparse_link_kernel(const HystParams p) {
         const unsigned int rel = g % fs;
         const int y = (int)(rel / (unsigned int)W), x = (int)(rel - (unsigned int)y * (unsigned int)W);
         const uint8_t* c = p.cls + g;
+        // the four forward neighbours' class bytes are fetched together (one round trip to L2 instead of up to three dependent
+        // ones); neighbours outside the image count as "not kept"
+        const bool has_e = x + 1 < W, has_s = y + 1 < Hh, has_w = x > 0;
         const int ca = c[0];
-        if (x + 1 < W) {
-            const int ce = c[1];
-            if (ce) sparse_link(p.parent, (int)g, ca, (int)g + 1, ce);
-        }
-        if (y + 1 < Hh) {
-            const int cs = c[W];
-            if (cs) {
-                sparse_link(p.parent, (int)g, ca, (int)g + W, cs);
-            } else {
-                const bool quirk = (p.row0 + y == 0) && (x == 1);   // (0,1) -> its SW neighbour (1,0)
-                if (x > 0 && !quirk) {
-                    const int cw = c[W - 1];
-                    if (cw) sparse_link(p.parent, (int)g, ca, (int)g + W - 1, cw);
-                }
-                if (x + 1 < W) {
-                    const int cx = c[W + 1];
-                    if (cx) sparse_link(p.parent, (int)g, ca, (int)g + W + 1, cx);
-                }
-            }
+        const int ce = has_e ? c[1] : 0;
+        const int cs = has_s ? c[W] : 0;
+        const bool quirk = (p.row0 + y == 0) && (x == 1);   // (0,1) -> its SW neighbour (1,0)
+        const int cw = (has_s && has_w && !quirk) ? c[W - 1] : 0;
+        const int cx = (has_s && has_e) ? c[W + 1] : 0;
+        if (ce) sparse_link(p.parent, (int)g, ca, (int)g + 1, ce);
+        if (cs) {
+            sparse_link(p.parent, (int)g, ca, (int)g + W, cs);
+        } else {
+            if (cw) sparse_link(p.parent, (int)g, ca, (int)g + W - 1, cw);
+            if (cx) sparse_link(p.parent, (int)g, ca, (int)g + W + 1, cx);
         }
     }
 }

@@ -40,6 +40,7 @@ SIGNATURES = {
     "b200_ctx_synchronize": (C.c_int, [_ctx]),
     "b200_ctx_set_chunk_frames": (C.c_int, [_ctx, C.c_int]),
     "b200_ctx_kernel_launches": (C.c_longlong, [_ctx]),
+    "b200_ctx_transfer_bytes": (C.c_int, [_ctx, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "b200_gaussian_window": (C.c_int, [C.c_float]),
     "b200_gaussian_kernel": (C.c_int, [C.c_float, _f32p, C.POINTER(C.c_int)]),
     "b200_direction_host": (C.c_int, [C.c_int, C.c_int]),

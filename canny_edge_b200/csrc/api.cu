@@ -5,8 +5,12 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <emmintrin.h>  // _mm_stream_si64 / _mm_sfence (SSE2, x86-64 baseline): non-temporal stores of the expanded edge map
+
 #include <algorithm>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 
 #include "canny_math.h"
 #include "internal.h"
@@ -111,6 +115,83 @@ int prepare_gauss(b200_ctx* ctx, float sigma) {
     g.radius = radius;
     return B200_OK;
 }
+
+// ---- host side of the bit-packed edge transfer ---------------------------------------------------------------
+// b200_canny_batch_host sends the edge map over PCIe as 1 bit per pixel (the link is the bottleneck of the host path: with both
+// directions carrying 1 B/px it saturates at ~46 GB/s each way) and expands it to the 0 / 255 bytes of the reference's result
+// on the host, with a small pool of threads that runs while the GPU works on the following chunks.
+struct UnpackPool {
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_go, cv_done;
+    const uint8_t* src = nullptr;
+    uint8_t* dst = nullptr;
+    size_t n_px = 0;
+    int generation = 0, pending = 0;
+    bool stop = false;
+    uint64_t lut[256];
+
+    explicit UnpackPool(int n_threads) {
+        for (int b = 0; b < 256; ++b) {
+            uint64_t v = 0;
+            for (int i = 0; i < 8; ++i) if (b & (1 << i)) v |= 0xFFull << (8 * i);
+            lut[b] = v;
+        }
+        for (int t = 0; t < n_threads; ++t) workers.emplace_back([this, t] { loop(t); });
+    }
+    ~UnpackPool() {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv_go.notify_all();
+        for (auto& w : workers) w.join();
+    }
+    int parts() const { return (int)workers.size() + 1; }
+    void slice(int part) {  // part-th of parts() slices, on 64-byte-of-output boundaries
+        const size_t n_bytes_in = n_px / 8;
+        const size_t per = ((n_bytes_in + parts() - 1) / parts() + 7) & ~(size_t)7;
+        const size_t b0 = std::min(n_bytes_in, per * (size_t)part), b1 = std::min(n_bytes_in, b0 + per);
+        if ((reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+            // streaming stores: the 64 bytes made from 8 input bytes fill one cache line, so the line is written without first
+            // being read (the host path is bound by host-memory traffic: PCIe reads the frames from the same DRAM)
+            long long* out = reinterpret_cast<long long*>(dst);
+            for (size_t i = b0; i < b1; ++i) _mm_stream_si64(out + i, (long long)lut[src[i]]);
+            _mm_sfence();
+        } else {
+            for (size_t i = b0; i < b1; ++i) memcpy(dst + 8 * i, &lut[src[i]], 8);
+        }
+        if (part == parts() - 1) {  // the last few pixels when n_px is not a multiple of 8
+            for (size_t px = 8 * n_bytes_in; px < n_px; ++px) dst[px] = ((src[px >> 3] >> (px & 7)) & 1) ? 255 : 0;
+        }
+    }
+    void loop(int t) {
+        int seen = 0;
+        while (true) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_go.wait(lk, [&] { return stop || generation != seen; });
+                if (stop) return;
+                seen = generation;
+            }
+            slice(t);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (--pending == 0) cv_done.notify_one();
+            }
+        }
+    }
+    // expands n_px bits at `s` into n_px bytes at `d`; returns when done (the caller's thread takes a slice too)
+    void run(const uint8_t* s, uint8_t* d, size_t n) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            src = s; dst = d; n_px = n;
+            pending = (int)workers.size();
+            ++generation;
+        }
+        cv_go.notify_all();
+        slice(parts() - 1);
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+};
 
 static std::mutex g_default_mu;
 static b200_ctx* g_default_ctx = nullptr;
@@ -232,6 +313,7 @@ int b200_ctx_create(int device, b200_ctx** out) {
     for (int i = 0; i < 3; ++i) {
         CB_CUDA(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
         CB_CUDA(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+        CB_CUDA(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming | cudaEventBlockingSync));
     }
     CB_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_kept), 4 * sizeof(unsigned int)));
@@ -249,7 +331,14 @@ int b200_ctx_destroy(b200_ctx* c) {
     rel(c->ws_planes, false); rel(c->ws_misc, false); rel(c->ws_band_parent, false); rel(c->ws_band_list, false); rel(c->ws_band_aux, false);
     if (c->gauss.d_w) cudaFree(c->gauss.d_w);
     if (c->h_kept) cudaFreeHost(c->h_kept);
-    for (int i = 0; i < 3; ++i) { if (c->side[i]) cudaStreamDestroy(c->side[i]); if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]); }
+    for (int i = 0; i < 3; ++i) {
+        if (c->side[i]) cudaStreamDestroy(c->side[i]);
+        if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+        if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
+        rel(c->dev_bits[i], false);
+        rel(c->host_bits[i], true);
+    }
+    delete c->pool;
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     {
@@ -274,6 +363,13 @@ int b200_ctx_synchronize(b200_ctx* ctx) {
 int b200_ctx_set_chunk_frames(b200_ctx* ctx, int frames) {
     CB_TRY(resolve_ctx(ctx));
     ctx->chunk_frames = frames < 0 ? 0 : frames;
+    return B200_OK;
+}
+int b200_ctx_transfer_bytes(const b200_ctx* ctx, unsigned long long* h2d, unsigned long long* d2h) {
+    if (!ctx) ctx = g_default_ctx;
+    if (!ctx || !h2d || !d2h) { set_error("bad argument"); return B200_ERR_INVALID_ARG; }
+    *h2d = ctx->h2d_bytes;
+    *d2h = ctx->d2h_bytes;
     return B200_OK;
 }
 long long b200_ctx_kernel_launches(const b200_ctx* ctx) {
@@ -470,30 +566,67 @@ int b200_canny_batch_host(b200_ctx* ctx, const uint8_t* frames, int n_frames, in
     CB_TRY(resolve_ctx(ctx));
     CB_TRY(prepare_gauss(ctx, sigma));
     const long long px = (long long)h * w;
-    // chunks of ~64 MB: big enough for full PCIe rate, small enough that three are in flight (H2D | kernels | D2H)
+    // chunks of ~64 MB: big enough for full PCIe rate, small enough that three are in flight (H2D | kernels | D2H + host unpack)
     int chunk = ctx->chunk_frames > 0 ? ctx->chunk_frames : (int)std::max<long long>(1, (64LL << 20) / px);
     chunk = std::min(chunk, n_frames);
     const int n_chunks = (n_frames + chunk - 1) / chunk;
     const int n_slots = std::min(3, n_chunks);
+    static const bool packed_off = [] { const char* e = getenv("B200_CANNY_NO_PACKED_D2H"); return e && e[0] == '1'; }();
+    // small jobs are latency-bound: the byte map goes back directly (no pack kernel, no host pass)
+    const bool packed = !packed_off && (long long)n_frames * px >= (8LL << 20);
+    const size_t chunk_bits_bytes = (((size_t)px * (size_t)chunk + 31) / 32) * 4;
     for (int s = 0; s < n_slots; ++s) {
         CB_TRY(ensure_ws(ctx->ws_parent[s], (size_t)px * 4 * (size_t)chunk));
         CB_TRY(ensure_ws(ctx->ws_list[s], list_bytes(chunk, h, w)));
         CB_TRY(ensure_ws(ctx->dev_in[s], (size_t)px * (size_t)chunk));
         CB_TRY(ensure_ws(ctx->dev_out[s], (size_t)px * (size_t)chunk));
+        if (packed) {
+            CB_TRY(ensure_ws(ctx->dev_bits[s], chunk_bits_bytes));
+            CB_TRY(ensure_ws(ctx->host_bits[s], chunk_bits_bytes, /*pinned_host=*/true));
+        }
+    }
+    if (packed && !ctx->pool) {
+        // measured on the 16-vCPU B200 hosts: 6 expanding threads (5 workers + the caller) keep up with the link; more of them
+        // only fight the DMA engine for host-memory bandwidth (e2e 50 Gpix/s with 6, 45 with 10, 34 with 16)
+        unsigned hc = std::thread::hardware_concurrency();
+        int n_threads = (int)std::min<unsigned>(std::max<unsigned>((hc ? hc : 4) / 2, 1), 6) - 1;
+        if (const char* e = getenv("B200_CANNY_UNPACK_THREADS")) n_threads = std::max(0, atoi(e) - 1);
+        ctx->pool = new UnpackPool(std::max(0, n_threads));
     }
     CB_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
     for (int s = 0; s < n_slots; ++s) CB_CUDA(cudaStreamWaitEvent(ctx->side[s], ctx->ev_fork, 0));
+    auto finish_chunk = [&](int c) -> int {  // host side of chunk c: wait for its packed map, expand it into the caller's buffer
+        const int f0 = c * chunk, nf = std::min(chunk, n_frames - f0);
+        const int s = c % n_slots;
+        CB_CUDA(cudaEventSynchronize(ctx->ev_chunk[s]));
+        ctx->pool->run(reinterpret_cast<const uint8_t*>(ctx->host_bits[s].ptr), edges + (long long)f0 * px, (size_t)px * nf);
+        return B200_OK;
+    };
     for (int c = 0; c < n_chunks; ++c) {
         const int f0 = c * chunk, nf = std::min(chunk, n_frames - f0);
         const int s = c % n_slots;
         cudaStream_t st = ctx->side[s];
         uint8_t* din = reinterpret_cast<uint8_t*>(ctx->dev_in[s].ptr);
         uint8_t* dout = reinterpret_cast<uint8_t*>(ctx->dev_out[s].ptr);
-        // stream order on `st` makes slot reuse safe: chunk c+n_slots' H2D waits for chunk c's D2H
+        // slot reuse: chunk c's device buffers are ordered by the stream; its pinned host_bits[s] was consumed by
+        // finish_chunk(c - n_slots), which ran before this iteration (see below)
         CB_CUDA(cudaMemcpyAsync(din, frames + (long long)f0 * px, (size_t)px * nf, cudaMemcpyHostToDevice, st));
+        ctx->h2d_bytes += (unsigned long long)px * nf;
+        ctx->d2h_bytes += packed ? (unsigned long long)(((size_t)px * nf + 31) / 32) * 4 : (unsigned long long)px * nf;
         CB_TRY(run_frames_device(ctx, st, s, din, dout, nf, h, w, lo, hi, nullptr, nullptr, nullptr, nullptr));
-        CB_CUDA(cudaMemcpyAsync(edges + (long long)f0 * px, dout, (size_t)px * nf, cudaMemcpyDeviceToHost, st));
+        if (packed) {
+            uint32_t* dbits = reinterpret_cast<uint32_t*>(ctx->dev_bits[s].ptr);
+            CB_TRY(launch_pack_edges(ctx, st, dout, dbits, (size_t)px * nf));
+            CB_CUDA(cudaMemcpyAsync(ctx->host_bits[s].ptr, dbits, (((size_t)px * nf + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
+            CB_CUDA(cudaEventRecord(ctx->ev_chunk[s], st));
+            // keep n_slots chunks in flight on the GPU; expand the oldest one while they run
+            if (c >= n_slots - 1) CB_TRY(finish_chunk(c - (n_slots - 1)));
+        } else {
+            CB_CUDA(cudaMemcpyAsync(edges + (long long)f0 * px, dout, (size_t)px * nf, cudaMemcpyDeviceToHost, st));
+        }
     }
+    if (packed)
+        for (int c = std::max(0, n_chunks - (n_slots - 1)); c < n_chunks; ++c) CB_TRY(finish_chunk(c));
     for (int s = 0; s < n_slots; ++s) {
         CB_CUDA(cudaEventRecord(ctx->ev_join[s], ctx->side[s]));
         CB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[s], 0));

@@ -402,6 +402,41 @@ __global__ void expand_u8_i16_kernel(const uint8_t* __restrict__ cls, int16_t* _
         out[i] = cls[i];
 }
 
+// 0 / 255 bytes -> 1 bit per pixel (bit i of byte k <-> pixel 8k + i): what b200_canny_batch_host sends over PCIe instead of
+// the byte map.  One thread per 32 pixels (two 128-bit loads, one 32-bit store).
+__global__ void pack_edges_kernel(const uint8_t* __restrict__ cls, uint32_t* __restrict__ bits, size_t n_px) {
+    const size_t n_words = (n_px + 31) / 32;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t out = 0;
+        if (32 * i + 32 <= n_px && ((reinterpret_cast<uintptr_t>(cls) & 15) == 0)) {
+            const uint4 a = __ldcs(reinterpret_cast<const uint4*>(cls + 32 * i));
+            const uint4 b = __ldcs(reinterpret_cast<const uint4*>(cls + 32 * i) + 1);
+            const uint32_t wv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t m = wv[k] & 0x01010101u;                 // bit 0 of each of the four bytes
+                const uint32_t nib = (m | (m >> 7) | (m >> 14) | (m >> 21)) & 0xFu;
+                out |= nib << (4 * k);
+            }
+        } else {
+            for (int k = 0; k < 32 && 32 * i + k < n_px; ++k) out |= (uint32_t)(cls[32 * i + k] & 1u) << k;
+        }
+        bits[i] = out;
+    }
+}
+
+int launch_pack_edges(b200_ctx* ctx, cudaStream_t st, const uint8_t* cls, uint32_t* bits, size_t n_px) {
+    const size_t n_words = (n_px + 31) / 32;
+    size_t b = (n_words + 255) / 256;
+    const size_t cap = 16 * (size_t)(ctx->sm_count > 0 ? ctx->sm_count : 148);
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    pack_edges_kernel<<<(int)b, 256, 0, st>>>(cls, bits, n_px);
+    CB_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return B200_OK;
+}
+
 static int grid_for(size_t n, const b200_ctx* ctx) {
     size_t b = (n + 255) / 256;
     size_t cap = 16 * (size_t)(ctx->sm_count > 0 ? ctx->sm_count : 148);

@@ -90,6 +90,8 @@ struct HystParams {
     const unsigned int* count;   // the list-driven kernels keep LAUNCH-relative indices (frame*frame_stride + pixel) in parent[]
 };
 
+struct UnpackPool;  // api.cu
+
 // ---- the context ------------------------------------------------------------------------------
 struct Workspace {
     void* ptr = nullptr;
@@ -122,10 +124,14 @@ struct b200_ctx {
     cb::Workspace ws_planes;      // stage-API scratch planes
     cb::Workspace ws_misc;
     cb::Workspace dev_in[3], dev_out[3];  // device staging for the batch_host pipeline
+    cb::Workspace dev_bits[3], host_bits[3];  // bit-packed edge maps of a chunk: device side and pinned host side
+    cudaEvent_t ev_chunk[3] = {nullptr, nullptr, nullptr};  // "chunk's packed map has arrived in host_bits[slot]"
+    cb::UnpackPool* pool = nullptr;       // host threads that expand the packed maps into the caller's byte buffer
     cb::Workspace ws_band_parent;         // union-find slots of the resident band (row-band sharding)
     cb::Workspace ws_band_aux;            // boundary roots of the resident band + the cross-band forest
     int chunk_frames = 0;
     long long launches = 0;
+    unsigned long long h2d_bytes = 0, d2h_bytes = 0;  // PCIe bytes moved by b200_canny_batch_host so far
     cb::Profiler prof;
     // band state (row-band sharding)
     int band_rows = 0, band_width = 0, band_row0 = 0;
@@ -175,6 +181,7 @@ int launch_ccl_resolve(b200_ctx* ctx, cudaStream_t st, const HystParams& p);  //
 int launch_classify_i16(b200_ctx* ctx, cudaStream_t st, const int16_t* nms, uint8_t* cls, size_t n,
                         int lo, int hi);
 int launch_expand_u8_to_i16(b200_ctx* ctx, cudaStream_t st, const uint8_t* cls, int16_t* out, size_t n);
+int launch_pack_edges(b200_ctx* ctx, cudaStream_t st, const uint8_t* cls, uint32_t* bits, size_t n_px);
 // stages.cu
 int launch_xy_gradient(b200_ctx* ctx, cudaStream_t st, const int16_t* blur, int h, int w, int16_t* gx,
                        int16_t* gy);

@@ -62,6 +62,9 @@ int b200_ctx_synchronize(b200_ctx* ctx);
 int b200_ctx_set_chunk_frames(b200_ctx* ctx, int frames);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 long long b200_ctx_kernel_launches(const b200_ctx* ctx);
+/* Bytes b200_canny_batch_host has moved over PCIe so far on this context, per direction (bench.py's e2e byte counts: the edge
+ * maps of jobs >= 8 Mpix come back bit-packed, 1 bit per pixel, and are expanded to 0 / 255 bytes on the host). */
+int b200_ctx_transfer_bytes(const b200_ctx* ctx, unsigned long long* h2d_bytes, unsigned long long* d2h_bytes);
 
 /* In every function below ctx may be NULL: a lazily created process-wide context on the current
  * CUDA device is used (what the reference-signature C++ shims in canny_b200_compat.hpp do). */
@@ -134,7 +137,9 @@ int b200_canny_steps(b200_ctx* ctx, const uint8_t* img, float sigma, int min_val
 
 /* n_frames independent frames, host memory in, host memory out (u8, 0/255).  What main.cpp's frame
  * loop (src/main.cpp:120-137) becomes for N frames: chunked, H2D / kernels / D2H overlapped on
- * separate streams through pinned staging.  frames: n_frames*height*width bytes. */
+ * separate streams.  frames: n_frames*height*width bytes.  Pinned (page-locked) buffers give the full
+ * PCIe rate; pageable ones work.  Jobs of >= 8 Mpix return the map over PCIe bit-packed and expand it
+ * into `edges` with a few host threads while the GPU works on the next chunk. */
 int b200_canny_batch_host(b200_ctx* ctx, const uint8_t* frames, int n_frames, int height, int width,
                           float sigma, int min_val, int max_val, uint8_t* edges);
 

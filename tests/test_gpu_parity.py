@@ -314,3 +314,24 @@ def test_sparse_hysteresis_long_chains(gpu_ctx, oracle):
         im = np.full((64, 64), 100, np.uint8)
         im[:4, :4] = rng.integers(0, 256, (4, 4))
         assert_same("corner", cb.cuda_canny(im, 0.5, 5, 120, ctx=gpu_ctx), oracle.canny(im, 0.5, 5, 120))
+
+
+def test_batch_host_bit_packed_transfer(oracle):
+    """Jobs of >= 8 Mpix return the edge map over PCIe as 1 bit per pixel and expand it on the host (thread pool): full-HD and an
+    odd size whose pixel count is not a multiple of 8 or 32, several chunks in flight, against the oracle and against the
+    byte-map transfer."""
+    import os
+    ctx = cb.Context(0)
+    try:
+        for n, h, w, chunk in ((5, 1080, 1920, 0), (9, 1001, 999, 2), (4, 2160, 3840, 1)):
+            frames = cb.synth_host(n, h, w, kind=0, seed=31 + n)
+            ctx.set_chunk_frames(chunk)
+            out = cb.canny_batch_host(frames, 1.4, 20, 60, ctx=ctx)
+            assert set(np.unique(out).tolist()) <= {0, 255}
+            for f in (0, n - 1):
+                assert_same(f"{n}x{h}x{w} frame {f}", out[f].astype(np.int16), oracle.canny(frames[f], 1.4, 20, 60))
+            dev = np.stack([cb.cuda_canny(frames[f], 1.4, 20, 60, ctx=ctx) for f in range(n)]).astype(np.uint8)
+            assert_same("packed vs single-frame API", out, dev)
+    finally:
+        ctx.set_chunk_frames(0)
+        ctx.close()

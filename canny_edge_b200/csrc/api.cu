@@ -586,10 +586,11 @@ int b200_canny_batch_host(b200_ctx* ctx, const uint8_t* frames, int n_frames, in
         }
     }
     if (packed && !ctx->pool) {
-        // measured on the 16-vCPU B200 hosts: 6 expanding threads (5 workers + the caller) keep up with the link; more of them
-        // only fight the DMA engine for host-memory bandwidth (e2e 50 Gpix/s with 6, 45 with 10, 34 with 16)
+        // measured on the 16-vCPU B200 hosts (tools/e2e_probe.py): 4 expanding threads (3 workers + the caller) keep up with the
+        // link; more of them only fight the DMA engine for host-memory bandwidth (e2e 52.7 Gpix/s with 4, 50 with 6-8, 45 with 10,
+        // 34 with 16)
         unsigned hc = std::thread::hardware_concurrency();
-        int n_threads = (int)std::min<unsigned>(std::max<unsigned>((hc ? hc : 4) / 2, 1), 6) - 1;
+        int n_threads = (int)std::min<unsigned>(std::max<unsigned>((hc ? hc : 4) / 2, 1), 4) - 1;
         if (const char* e = getenv("B200_CANNY_UNPACK_THREADS")) n_threads = std::max(0, atoi(e) - 1);
         ctx->pool = new UnpackPool(std::max(0, n_threads));
     }

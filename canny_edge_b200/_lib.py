@@ -52,6 +52,8 @@ SIGNATURES = {
     "b200_hysteresis": (C.c_int, [_ctx, _i16p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "b200_canny": (C.c_int, [_ctx, _u8p, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, _i16p]),
     "b200_canny_steps": (C.c_int, [_ctx, _u8p, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, _i16p, _i16p, _i16p, _i16p, _i16p]),
+    "b200_canny_bgr": (C.c_int, [_ctx, _u8p, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, _i16p]),
+    "b200_bgr_to_gray_device": (C.c_int, [_ctx, _u8p, C.c_size_t, _u8p]),
     "b200_canny_batch_host": (C.c_int, [_ctx, _u8p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _u8p]),
     "b200_canny_batch_device": (C.c_int, [_ctx, _u8p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _u8p]),
     "b200_profile_stages_device": (C.c_int, [_ctx, _u8p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _u8p, C.POINTER(C.c_float), C.POINTER(C.c_int)]),

@@ -151,6 +151,20 @@ def cuda_canny(img, sigma: float, min_val: int, max_val: int, steps: bool = Fals
     return blur, mag, ang, nms, edges
 
 
+def cuda_canny_bgr(frame, sigma: float, min_val: int, max_val: int, return_gray: bool = False, ctx: Optional[Context] = None):
+    """One interleaved B,G,R frame (h, w, 3) as cv2 / cv::Mat hold it: cvtColor(BGR2GRAY) + cuda_canny on the GPU — the
+    reference's per-frame work, src/main.cpp:113,128.  Returns the int16 0/255 map (and the uint8 gray plane when asked)."""
+    a = np.ascontiguousarray(frame, dtype=np.uint8)
+    if a.ndim != 3 or a.shape[2] != 3:
+        raise ValueError("expected a (height, width, 3) BGR frame")
+    h, w = a.shape[:2]
+    edges = np.empty((h, w), np.int16)
+    gray = np.empty((h, w), np.uint8) if return_gray else None
+    check(load().b200_canny_bgr(_h(ctx), _ptr(a), C.c_float(sigma), int(min_val), int(max_val), h, w,
+                                _ptr(gray) if return_gray else None, _ptr(edges)))
+    return (edges, gray) if return_gray else edges
+
+
 # ---------------------------------------------------------------------------------------------------
 # batched
 # ---------------------------------------------------------------------------------------------------

@@ -524,6 +524,34 @@ int b200_canny(b200_ctx* ctx, const uint8_t* img, float sigma, int lo, int hi, i
     return b200_canny_steps(ctx, img, sigma, lo, hi, h, w, nullptr, nullptr, nullptr, nullptr, edges);
 }
 
+int b200_bgr_to_gray_device(b200_ctx* ctx, const uint8_t* d_bgr, size_t n_px, uint8_t* d_gray) {
+    if (!d_bgr || !d_gray || n_px == 0) { set_error("bad argument to b200_bgr_to_gray_device"); return B200_ERR_INVALID_ARG; }
+    CB_TRY(resolve_ctx(ctx));
+    return launch_bgr_to_gray(ctx, ctx->stream, d_bgr, d_gray, n_px);
+}
+
+int b200_canny_bgr(b200_ctx* ctx, const uint8_t* bgr, float sigma, int lo, int hi, int h, int w, uint8_t* gray_out, int16_t* edges) {
+    CB_TRY(check_image(bgr, edges, h, w));
+    CB_TRY(resolve_ctx(ctx));
+    CB_TRY(prepare_gauss(ctx, sigma));
+    const long long px = (long long)h * w;
+    Planes pl;
+    CB_TRY(get_planes(ctx, px, pl));
+    CB_TRY(ensure_ws(ctx->ws_parent[0], (size_t)px * 4));
+    CB_TRY(ensure_ws(ctx->ws_list[0], list_bytes(1, h, w)));
+    cudaStream_t st = ctx->stream;
+    // the 3-byte frame is staged in the int16 scratch planes (p16[0..1] hold 4*px bytes >= 3*px)
+    uint8_t* d_bgr = reinterpret_cast<uint8_t*>(pl.p16[0]);
+    CB_CUDA(cudaMemcpyAsync(d_bgr, bgr, (size_t)px * 3, cudaMemcpyHostToDevice, st));
+    CB_TRY(launch_bgr_to_gray(ctx, st, d_bgr, pl.in, (size_t)px));
+    CB_TRY(run_frames_device(ctx, st, 0, pl.in, pl.cls, 1, h, w, lo, hi, nullptr, nullptr, nullptr, nullptr));
+    CB_TRY(launch_expand_u8_to_i16(ctx, st, pl.cls, pl.p16[4], (size_t)px));
+    if (gray_out) CB_CUDA(cudaMemcpyAsync(gray_out, pl.in, (size_t)px, cudaMemcpyDeviceToHost, st));
+    CB_CUDA(cudaMemcpyAsync(edges, pl.p16[4], (size_t)px * 2, cudaMemcpyDeviceToHost, st));
+    CB_CUDA(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
 // ---- batched --------------------------------------------------------------------------------------------
 int b200_canny_batch_device(b200_ctx* ctx, const uint8_t* d_frames, int n_frames, int h, int w, float sigma, int lo,
                             int hi, uint8_t* d_edges) {

@@ -189,6 +189,7 @@ int launch_sobel(b200_ctx* ctx, cudaStream_t st, const int16_t* blur, int h, int
                  int16_t* ang);
 int launch_nonmaximal(b200_ctx* ctx, cudaStream_t st, const int16_t* mag, const int16_t* ang, int h,
                       int w, int16_t* out);
+int launch_bgr_to_gray(b200_ctx* ctx, cudaStream_t st, const uint8_t* bgr, uint8_t* gray, size_t n_px);
 // synth.cu
 int launch_synth(b200_ctx* ctx, cudaStream_t st, uint8_t* d, int n_frames, int row0, int rows, int width,
                  int kind, uint64_t seed, int first_frame);

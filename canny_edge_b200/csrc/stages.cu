@@ -119,4 +119,47 @@ int launch_nonmaximal(b200_ctx* ctx, cudaStream_t st, const int16_t* mag, const 
     return B200_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// BGR -> gray: the step right before the hot path in the reference (cvtColor(frame, gray, COLOR_BGR2GRAY), src/main.cpp:113).
+// OpenCV's 8-bit path is fixed point: (B*3735 + G*19235 + R*9798 + 2^14) >> 15 (coefficients 0.114 / 0.587 / 0.299 in 15 bits);
+// tests/test_bgr.py checks the kernel against cv2.cvtColor itself.  One thread per 4 pixels: three 32-bit loads, one 32-bit store.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t gray_of(uint32_t b, uint32_t g, uint32_t r) { return (b * 3735u + g * 19235u + r * 9798u + 16384u) >> 15; }
+
+__global__ void bgr_to_gray_kernel(const uint8_t* __restrict__ bgr, uint8_t* __restrict__ gray, size_t n_px) {
+    const size_t n4 = n_px / 4;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(bgr) | reinterpret_cast<uintptr_t>(gray)) & 3) == 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        if (aligned) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(bgr) + 3 * i;
+            const uint32_t w0 = __ldcs(src), w1 = __ldcs(src + 1), w2 = __ldcs(src + 2);   // B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
+            const uint32_t g0 = gray_of(w0 & 255, (w0 >> 8) & 255, (w0 >> 16) & 255);
+            const uint32_t g1 = gray_of(w0 >> 24, w1 & 255, (w1 >> 8) & 255);
+            const uint32_t g2 = gray_of((w1 >> 16) & 255, w1 >> 24, w2 & 255);
+            const uint32_t g3 = gray_of((w2 >> 8) & 255, (w2 >> 16) & 255, w2 >> 24);
+            reinterpret_cast<uint32_t*>(gray)[i] = g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
+        } else {
+            for (int k = 0; k < 4; ++k) {
+                const uint8_t* px = bgr + 3 * (4 * i + k);
+                gray[4 * i + k] = (uint8_t)gray_of(px[0], px[1], px[2]);
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n_px & 3)) {
+        const size_t i = (n_px & ~(size_t)3) + threadIdx.x;
+        gray[i] = (uint8_t)gray_of(bgr[3 * i], bgr[3 * i + 1], bgr[3 * i + 2]);
+    }
+}
+
+int launch_bgr_to_gray(b200_ctx* ctx, cudaStream_t st, const uint8_t* bgr, uint8_t* gray, size_t n_px) {
+    size_t blocks = (n_px / 4 + 255) / 256;
+    const size_t cap = 32 * (size_t)(ctx->sm_count > 0 ? ctx->sm_count : 148);
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    bgr_to_gray_kernel<<<(int)blocks, 256, 0, st>>>(bgr, gray, n_px);
+    CB_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return B200_OK;
+}
+
 }  // namespace cb

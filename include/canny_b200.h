@@ -133,6 +133,16 @@ int b200_canny_steps(b200_ctx* ctx, const uint8_t* img, float sigma, int min_val
                      int height, int width, int16_t* blur, int16_t* magnitude, int16_t* angle,
                      int16_t* nms, int16_t* edges);
 
+/* cvtColor(frame, gray, COLOR_BGR2GRAY) + cuda_canny — what the reference's frame loop does per frame (src/main.cpp:113,128),
+ * with the colour conversion moved onto the GPU.  bgr: height*width*3 bytes, interleaved B,G,R as cv::Mat stores them.  The
+ * gray values are OpenCV's 8-bit fixed-point ones ((B*3735 + G*19235 + R*9798 + 2^14) >> 15), bit for bit.  gray_out may be
+ * NULL; when given it receives the height*width gray plane the pipeline ran on. */
+int b200_canny_bgr(b200_ctx* ctx, const uint8_t* bgr, float sigma, int min_val, int max_val, int height, int width,
+                   uint8_t* gray_out, int16_t* edges);
+/* The conversion alone on DEVICE memory (n_px pixels; d_bgr 3*n_px bytes, d_gray n_px bytes), asynchronous on the
+ * context's stream: for callers whose decoder already leaves BGR frames in HBM. */
+int b200_bgr_to_gray_device(b200_ctx* ctx, const uint8_t* d_bgr, size_t n_px, uint8_t* d_gray);
+
 /* ------------------------------------------------------------------ batched, u8 edge maps ------ */
 
 /* n_frames independent frames, host memory in, host memory out (u8, 0/255).  What main.cpp's frame

@@ -108,8 +108,9 @@ int prepare_gauss(b200_ctx* ctx, float sigma) {
         for (float v : g.w) wmin = v < wmin ? v : wmin;
         g.tiny = !((double)wmin * (double)wmin >= 8.077935669463161e-28);  // 2^-90
     }
-    g.div3_ok = false;
-    if (!g.tiny) CB_TRY(check_div3_device(ctx, g.count[0], g.count[(size_t)n1 * n1], &g.div3_ok));
+    g.div_mode = 5;
+    g.div_c = (float)(1.0 / (double)g.count[0] - 1.0);
+    if (!g.tiny) CB_TRY(check_div_mode_device(ctx, g.count[0], g.count[(size_t)n1 * n1], &g.div_c, &g.div_mode));
     g.sigma = sigma;
     g.window = window;
     g.radius = radius;

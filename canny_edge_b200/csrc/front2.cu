@@ -74,11 +74,12 @@ __host__ __device__ constexpr SmemLayout smem_layout(int radius) {
 }
 static_assert(kVuRows * kNpPitch * 4 <= kSlab * kTempPitch * 4, "the n-plane must fit into the free rows of the temp buffer");
 
-// RN(a / b) for the interior count: y = RN(1/b).  DIV3 is only instantiated when the host has checked, for this
-// very b and every float mantissa, that one Markstein correction already gives the IEEE quotient.
-template <bool DIV3>
-__device__ __forceinline__ float div_const(float a, float b, float y) {
-    if (DIV3) {
+// RN(a / b) for the interior count: y = RN(1/b), c = RN(1/b - 1).  The 1- and 3-instruction forms are only used when the host
+// has checked on the device, for this very b and every float mantissa, that they give the IEEE quotient (check_div_mode_device).
+template <int DIV>
+__device__ __forceinline__ float div_const(float a, float b, float y, float c) {
+    if (DIV == 1) return __fmaf_rn(a, c, a);
+    if (DIV == 3) {
         const float q = __fmul_rn(a, y);
         const float r = __fmaf_rn(-b, q, a);
         return __fmaf_rn(r, y, q);
@@ -92,7 +93,7 @@ __device__ __forceinline__ int trunc_biased(float q) { return __float_as_int(__f
 constexpr int kBias = 0x4B000000;
 constexpr int kBias4 = (int)(4u * 0x4B000000u);  // 4 * bias mod 2^32 = 0x2C000000
 
-template <int R, bool USE_TMA, bool DIV3>
+template <int R, bool USE_TMA, int DIV>
 __global__ void __launch_bounds__(kThreads, 2)
 front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -261,7 +262,7 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
                         // divide by the in-image weight sum (src/utils.cpp:47) and store four outputs
                         if (x_interior) {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) grp[e] = div_const<DIV3>(grp[e], cnt_full, rcp_full);
+                            for (int e = 0; e < 4; ++e) grp[e] = div_const<DIV>(grp[e], cnt_full, rcp_full, p.div_c);
                         } else {
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
@@ -296,7 +297,7 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
                 blur_run<R, kRunCol>(
                     ws, [&](int i) { return tcol[i * kTempPitch]; },
                     [&](int o, float s) {
-                        const int t2 = trunc_biased(div_const<DIV3>(s, cnt_full, rcp_full));
+                        const int t2 = trunc_biased(div_const<DIV>(s, cnt_full, rcp_full, p.div_c));
                         if (o >= 2) {
                             const int u = t2 - t0;                        // B[r+1] - B[r-1]
                             const int v4 = t0 + 2 * t1 + t2 - kBias4;     // B[r-1] + 2 B[r] + B[r+1]
@@ -540,17 +541,17 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int R, bool USE_TMA, bool DIV3>
+template <int R, bool USE_TMA, int DIV>
 static int launch_one2(b200_ctx* ctx, cudaStream_t st, const FrontParams& p, const CUtensorMap& tmap, dim3 grid) {
     const f2::SmemLayout L = f2::smem_layout(R);
     static bool configured[64] = {false};  // per instantiation, per device
     if (!configured[ctx->device & 63]) {
-        CB_CUDA(cudaFuncSetAttribute(f2::front2_kernel<R, USE_TMA, DIV3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        CB_CUDA(cudaFuncSetAttribute(f2::front2_kernel<R, USE_TMA, DIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
         configured[ctx->device & 63] = true;
     }
     {
         ProfScope ps(ctx, st, 0);
-        f2::front2_kernel<R, USE_TMA, DIV3><<<grid, f2::kThreads, L.total, st>>>(p, tmap);
+        f2::front2_kernel<R, USE_TMA, DIV><<<grid, f2::kThreads, L.total, st>>>(p, tmap);
     }
     CB_CUDA(cudaGetLastError());
     ctx->launches++;
@@ -558,9 +559,14 @@ static int launch_one2(b200_ctx* ctx, cudaStream_t st, const FrontParams& p, con
 }
 
 template <int R>
-static int launch_r2(b200_ctx* ctx, cudaStream_t st, const FrontParams& p, const CUtensorMap& tmap, dim3 grid, bool use_tma, bool div3) {
-    if (use_tma) return div3 ? launch_one2<R, true, true>(ctx, st, p, tmap, grid) : launch_one2<R, true, false>(ctx, st, p, tmap, grid);
-    return div3 ? launch_one2<R, false, true>(ctx, st, p, tmap, grid) : launch_one2<R, false, false>(ctx, st, p, tmap, grid);
+static int launch_r2(b200_ctx* ctx, cudaStream_t st, const FrontParams& p, const CUtensorMap& tmap, dim3 grid, bool use_tma, int div) {
+    if (use_tma) {
+        if (div == 1) return launch_one2<R, true, 1>(ctx, st, p, tmap, grid);
+        if (div == 3) return launch_one2<R, true, 3>(ctx, st, p, tmap, grid);
+        return launch_one2<R, true, 5>(ctx, st, p, tmap, grid);
+    }
+    // generic staging (odd widths) is not a throughput path: one instantiation, the always-valid division
+    return launch_one2<R, false, 5>(ctx, st, p, tmap, grid);
 }
 
 bool front2_supports(int radius) {
@@ -600,7 +606,8 @@ int launch_front2(b200_ctx* ctx, cudaStream_t st, const FrontParams& p_in) {
     CUtensorMap tmap;
     bool use_tma = false;
     CB_TRY(make_input_tensor_map(p, f2::in_pitch_for(radius), f2::kSlab, &tmap, &use_tma));
-    const bool div3 = ctx->gauss.div3_ok;
+    const int div3 = ctx->gauss.div_mode;
+    p.div_c = ctx->gauss.div_c;
     switch (radius) {
         case 2: return launch_r2<2>(ctx, st, p, tmap, grid, use_tma, div3);
         case 3: return launch_r2<3>(ctx, st, p, tmap, grid, use_tma, div3);

@@ -40,8 +40,10 @@ struct GaussTables {
     float* d_w = nullptr;      // device copies (owned by the context)
     float* d_count = nullptr;
     bool tiny = false;         // min weight^2 < 2^-90: blur sums may approach the subnormal range
-    bool div3_ok = false;      // one Markstein correction already gives RN(a / count_full) for EVERY float mantissa
-                               // (checked exhaustively on the device when the tables are built)
+    int div_mode = 5;          // cheapest exact form of RN(a / count_full), checked for EVERY float mantissa on the device when
+                               // the tables are built: 1 = fma(a, c, a) with c = RN(1/count - 1); 3 / 5 = one / two Markstein
+                               // corrections of a * RN(1/count)
+    float div_c = 0.f;         // c of the one-instruction form
 };
 
 // ---- parameters of the fused front kernel -----------------------------------------------------
@@ -68,6 +70,7 @@ struct FrontParams {
     int lo2, hi2;           // thresholds in squared-magnitude space (see front.cu)
     int lo, hi;             // raw thresholds (spill / zero-class decisions)
     int cls_zero;           // class of a suppressed pixel (value 0): nonzero only when lo <= 0
+    float div_c;            // front2: c of the one-instruction interior division (GaussTables::div_c)
     int ieee_div;           // 1: weights so small that sums can fall below 2^-100 -> use IEEE division instead of div_exact
     int tiles_x, tiles_y;
     // sparse hand-over to the hysteresis kernels (front2.cu only; both null -> not produced):
@@ -173,7 +176,7 @@ int make_input_tensor_map(const FrontParams& p, int box_cols, int box_rows, CUte
 bool front2_supports(int radius);
 int launch_front2(b200_ctx* ctx, cudaStream_t st, const FrontParams& p);
 // selftest.cu
-int check_div3_device(b200_ctx* ctx, float b, float y, bool* ok);
+int check_div_mode_device(b200_ctx* ctx, float b, float y, float* c, int* mode);
 // hysteresis.cu
 int launch_hysteresis(b200_ctx* ctx, cudaStream_t st, const HystParams& p);   // label + resolve
 int launch_ccl_label(b200_ctx* ctx, cudaStream_t st, const HystParams& p);    // tile-local forest + tile-boundary unions

@@ -1,5 +1,7 @@
 // selftest.cu — device-side table dumps used by the GPU tests to check the exact-arithmetic
 // building blocks of front.cu over their WHOLE domain (not just on images).
+#include <math.h>
+
 #include "canny_math.h"
 #include "exact_math.cuh"
 #include "internal.h"
@@ -53,18 +55,37 @@ __global__ void div3_check_kernel(float b, float y, unsigned long long* __restri
     if (bad) atomicAdd(mismatches, bad);
 }
 
-int check_div3_device(b200_ctx* ctx, float b, float y, bool* ok) {
-    *ok = false;
+// same question for the ONE-instruction form q = fma(a, c, a) with c = RN(1/b - 1): the interior count is 1 +- an ulp or two, so
+// a/b = a + a*(1/b - 1) and the fused multiply-add rounds that once.  Whether this single rounding always lands on RN(a/b)
+// depends on b; it is decided by trying every mantissa.
+__global__ void div1_check_kernel(float b, float c, unsigned long long* __restrict__ mismatches) {
+    unsigned long long bad = 0;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (1u << 23); i += gridDim.x * blockDim.x) {
+        const float a = __uint_as_float(0x3F800000u | i);
+        if (__float_as_uint(__fmaf_rn(a, c, a)) != __float_as_uint(__fdiv_rn(a, b))) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+// *mode = 1 (q = fma(a, c, a)), 3 (one Markstein correction) or 5 (two): the cheapest form that equals IEEE division by b for
+// every float mantissa.  For the one-instruction form the three floats around 1/b - 1 are tried (*c is the nearest on entry and
+// the one that works on return): which of them makes the single rounding land on RN(a/b) everywhere depends on b.
+int check_div_mode_device(b200_ctx* ctx, float b, float y, float* c, int* mode) {
+    *mode = 5;
     CB_TRY(ensure_ws(ctx->ws_misc, 256));
     unsigned long long* d = reinterpret_cast<unsigned long long*>(ctx->ws_misc.ptr);
-    unsigned long long h = 1;
-    CB_CUDA(cudaMemsetAsync(d, 0, sizeof(*d), ctx->stream));
-    div3_check_kernel<<<1184, 256, 0, ctx->stream>>>(b, y, d);
+    unsigned long long h[4] = {1, 1, 1, 1};
+    const float cand[3] = {*c, nextafterf(*c, INFINITY), nextafterf(*c, -INFINITY)};
+    CB_CUDA(cudaMemsetAsync(d, 0, 4 * sizeof(*d), ctx->stream));
+    for (int k = 0; k < 3; ++k) div1_check_kernel<<<1184, 256, 0, ctx->stream>>>(b, cand[k], d + k);
+    div3_check_kernel<<<1184, 256, 0, ctx->stream>>>(b, y, d + 3);
     CB_CUDA(cudaGetLastError());
-    ctx->launches++;
-    CB_CUDA(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->launches += 4;
+    CB_CUDA(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     CB_CUDA(cudaStreamSynchronize(ctx->stream));
-    *ok = (h == 0);
+    for (int k = 0; k < 3; ++k)
+        if (h[k] == 0) { *mode = 1; *c = cand[k]; return B200_OK; }
+    *mode = (h[3] == 0) ? 3 : 5;
     return B200_OK;
 }
 
@@ -125,6 +146,14 @@ int b200_division_check_device(b200_ctx* ctx, float sigma, unsigned long long* m
     ctx->launches++;
     CB_CUDA(cudaMemcpyAsync(mismatches, d, sizeof(*d), cudaMemcpyDeviceToHost, ctx->stream));
     CB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+
+int b200_division_mode_device(b200_ctx* ctx, float sigma, int* mode) {
+    if (!ctx || !mode) { set_error("bad argument"); return B200_ERR_INVALID_ARG; }
+    CB_CUDA(cudaSetDevice(ctx->device));
+    CB_TRY(prepare_gauss(ctx, sigma));
+    *mode = ctx->gauss.div_mode;
     return B200_OK;
 }
 

@@ -228,6 +228,10 @@ int b200_direction_table_host(int gmax, int16_t* out);
 int b200_direction_table_device(b200_ctx* ctx, int gmax, int16_t* out_host);
 int b200_isqrt_table_device(b200_ctx* ctx, int n_max, int32_t* out_host);
 int b200_division_check_device(b200_ctx* ctx, float sigma, unsigned long long* mismatches);
+/* Which exact form of sum / count the fused kernel uses for sigma's interior count, as decided by an exhaustive device check
+ * over all 2^23 float mantissas when the tables are built: 1 = fma(a, RN(1/count - 1), a), 3 = one Markstein correction of
+ * a * RN(1/count), 5 = two corrections (always valid). */
+int b200_division_mode_device(b200_ctx* ctx, float sigma, int* mode);
 
 /* Device-side count of 255 bytes in a u8 buffer (edge pixels), written to *count. */
 int b200_count_edges_device(b200_ctx* ctx, const uint8_t* d_edges, size_t n, unsigned long long* count);

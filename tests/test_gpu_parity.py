@@ -217,6 +217,21 @@ def test_division_exact(gpu_ctx, sigma):
     assert bad.value == 0
 
 
+def test_division_modes(gpu_ctx, oracle):
+    # the form of sum/count picked per sigma (exhaustive device check) must be one of the three, and whatever it is the blurred
+    # plane of a frame that exercises every quotient magnitude must match the oracle through the FUSED kernel (edges) as well
+    modes = {}
+    for sigma in (0.5, 0.8, 1.0, 1.4, 2.0, 3.0, 5.0):
+        m = C.c_int(0)
+        check(load().b200_division_mode_device(gpu_ctx.handle, C.c_float(sigma), C.byref(m)))
+        assert m.value in (1, 3, 5)
+        modes[sigma] = m.value
+        ramp = np.add.outer(np.arange(192), np.arange(320)).astype(np.int64)
+        img = ((ramp * 7 + (ramp // 3) ** 2) % 256).astype(np.uint8)
+        assert_same(f"sigma={sigma} mode={m.value}", cb.cuda_canny(img, sigma, 20, 60, ctx=gpu_ctx), oracle.canny(img, sigma, 20, 60))
+    print("division modes:", modes)
+
+
 # ------------------------------------------------------------------ batched / full-size
 def test_batch_matches_single_and_oracle(gpu_ctx, oracle):
     frames = cb.synth_host(5, 270, 480, kind=0, seed=42)

@@ -30,13 +30,12 @@ namespace cb {
 namespace f2 {
 
 constexpr int kThreads = 256;
-constexpr int kSlab = 64;        // rows per marching step (one TMA box)
+// rows per marching step (one TMA box) is the template parameter SLAB (64; 32 also builds, see launch_front2)
 constexpr int kTC = 128;         // computed columns per strip (temp / VU lines); column j <-> image x = x0 - 2 + j
 constexpr int kTW = kTC - 4;     // class-map columns produced per strip (Sobel + NMS eat 2 per side)
 constexpr int kTempPitch = 132;  // floats; == 4 mod 32: the row pass's 128-bit stores (lane = row) hit 8 distinct bank groups
 constexpr int kVuPitch = 132;    // int32 words; lane 31 of the last phase reads 4 words past column 127
-constexpr int kRunRow = 32;      // outputs per thread in the row pass
-constexpr int kRunCol = 34;      // blurred rows per thread in the column pass (32 VU rows need 34 blurred rows)
+// outputs per thread: SLAB/2 in the row pass, SLAB/2 VU rows = SLAB/2 + 2 blurred rows in the column pass
 
 __host__ __device__ constexpr int in_pitch_for(int radius) {
     // bytes per staged input row: up to 15 leading bytes (the TMA box starts on a 16 B boundary of the image
@@ -46,25 +45,25 @@ __host__ __device__ constexpr int in_pitch_for(int radius) {
     if ((k & 1) == 0) k += 1;
     return 16 * k;
 }
-__host__ __device__ constexpr int temp_rows_for(int radius) { return kSlab + 2 * radius + 2; }
-constexpr int kVuRows = kSlab + 2;
-
-constexpr int kNpPitch = 128;    // n-plane words per row: 66 rows x 128 words == the 64 free rows of the temp buffer
-constexpr int kEntPerWarp = (kSlab / 8) * 32;  // candidate list of one warp: at most one entry per (class row of that warp, lane)
-constexpr int kMaxEnt = 8 * kEntPerWarp;
+constexpr int kNpPitch = 128;    // n-plane words per row: (SLAB+2) rows x 128 words live in the temp rows phase 1 refills next slab
+__host__ __device__ constexpr int temp_rows_for(int radius, int slab) {
+    // 2R+2 tail rows + the slab's rows, and enough of them that the n-plane fits behind the tail
+    const int need = ((slab + 2) * kNpPitch + kTempPitch - 1) / kTempPitch;
+    return 2 * radius + 2 + (need > slab ? need : slab);
+}
 
 struct SmemLayout {
     int in_off, temp_off, vu_off, ent_off, bits_off, tab_off, w_off, bar_off, total;
 };
-__host__ __device__ constexpr SmemLayout smem_layout(int radius) {
+__host__ __device__ constexpr SmemLayout smem_layout(int radius, int slab) {
     SmemLayout L{};
     int o = 0;
-    L.in_off = o;   o += 2 * kSlab * in_pitch_for(radius);
+    L.in_off = o;   o += 2 * slab * in_pitch_for(radius);
     o = (o + 127) & ~127;
-    L.temp_off = o; o += temp_rows_for(radius) * kTempPitch * 4;
-    L.vu_off = o;   o += kVuRows * kVuPitch * 4;
-    L.ent_off = o;  o += kMaxEnt * 2;
-    L.bits_off = o; o += kSlab * 4 * 4;                        // kept-pixel bitmap of the slab's class rows: 4 words per row
+    L.temp_off = o; o += temp_rows_for(radius, slab) * kTempPitch * 4;
+    L.vu_off = o;   o += (slab + 2) * kVuPitch * 4;
+    L.ent_off = o;  o += slab * 32 * 2;                        // candidate lists: at most one 16-bit entry per (class row, lane)
+    L.bits_off = o; o += slab * 4 * 4;                         // kept-pixel bitmap of the slab's class rows: 4 words per row
     L.tab_off = o;  o += 2 * (radius + 1) * (radius + 1) * 4;  // count table, reciprocal table
     L.w_off = o;    o += (2 * radius + 1) * 4;
     o = (o + 15) & ~15;
@@ -72,7 +71,6 @@ __host__ __device__ constexpr SmemLayout smem_layout(int radius) {
     L.total = o;
     return L;
 }
-static_assert(kVuRows * kNpPitch * 4 <= kSlab * kTempPitch * 4, "the n-plane must fit into the free rows of the temp buffer");
 
 // RN(a / b) for the interior count: y = RN(1/b), c = RN(1/b - 1).  The 1- and 3-instruction forms are only used when the host
 // has checked on the device, for this very b and every float mantissa, that they give the IEEE quotient (check_div_mode_device).
@@ -93,11 +91,19 @@ __device__ __forceinline__ int trunc_biased(float q) { return __float_as_int(__f
 constexpr int kBias = 0x4B000000;
 constexpr int kBias4 = (int)(4u * 0x4B000000u);  // 4 * bias mod 2^32 = 0x2C000000
 
-template <int R, bool USE_TMA, int DIV>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int R, bool USE_TMA, int DIV, int SLAB>
+__global__ void __launch_bounds__(kThreads, (SLAB == 64 ? 2 : 4))
 front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    constexpr SmemLayout L = smem_layout(R);
+    constexpr int kSlab = SLAB;
+    constexpr int kRunRow = SLAB / 2;          // outputs per thread in the row pass: (SLAB rows) x (128 / kRunRow segments) = 256 threads
+    constexpr int kRunV = SLAB / 2;            // VU rows per thread in the column pass: 128 columns x 2 halves = 256 threads
+    constexpr int kRunCol = kRunV + 2;         // ... which need two more blurred rows
+    constexpr int kVuRows = SLAB + 2;
+    constexpr int kEntPerWarp = (SLAB / 8) * 32;
+    static_assert(SLAB == 32 || SLAB == 64, "row/column pass mappings are written for 32- and 64-row slabs");
+    static_assert(2 * R + 2 <= SLAB, "the saved tail must not overlap the rows it is copied from");
+    constexpr SmemLayout L = smem_layout(R, SLAB);
     constexpr int in_pitch = in_pitch_for(R);
     constexpr int T0 = 2 * R + 2;  // temp buffer row of the first row of the current slab
 
@@ -134,7 +140,7 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
         s_rcp[i] = p.count[(R + 1) * (R + 1) + i];
     }
     for (int i = tid; i < 2 * R + 1; i += kThreads) s_w[i] = p.w[i];
-    s_bits[tid] = 0;                                             // kThreads == kSlab * 4 words
+    if (tid < 4 * kSlab) s_bits[tid] = 0;
     if (USE_TMA && tid == 0) {
         mbar_init(bar0, 1);
         mbar_init(bar0 + 8, 1);
@@ -211,15 +217,16 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
         // ===================== phase 1: row blur, u8 -> f32 (src/utils.cpp:37-49) =====================
         // thread = (slab row 32*(warp>>2) + lane, 32 columns starting at 32*(warp&3)); temp buffer row T0 + slab row
         {
-            const int srow = 32 * (warp >> 2) + lane;
-            const int seg = warp & 3;
+            constexpr int kSegs = kTC / kRunRow;              // 4 segments of 32 columns (SLAB 64) or 8 of 16 (SLAB 32)
+            const int srow = 32 * (warp / kSegs) + lane;
+            const int seg = warp % kSegs;
             // needed bytes of this line: [32*seg + lead, 32*seg + lead + 32 + 2R).  lead = 4*dq + DR with DR a compile-time
             // constant (x0 is a multiple of 4) and dq uniform over the CTA: load aligned 128-bit vectors, shift by dq
             // WORDS with a uniform switch, pick bytes with static selectors.
             constexpr int DR = (((-2 - R) % 4) + 4) % 4;
             constexpr int KW = (DR + kRunRow + 2 * R + 3) / 4;   // words holding the needed bytes
             constexpr int NV = (KW + 3 + 3) / 4;                 // vectors covering KW + 3 words
-            static_assert(32 * 3 + 16 * NV <= in_pitch, "row pass would read past the staged line");
+            static_assert((kTC - kRunRow) + 16 * NV <= in_pitch, "row pass would read past the staged line");
             uint32_t wv[NV * 4];
             const uint4* src = reinterpret_cast<const uint4*>(slab + srow * in_pitch + seg * kRunRow);
 #pragma unroll
@@ -287,9 +294,9 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
         {
             const int c = tid & (kTC - 1);
             const int half = tid >> 7;
-            const float* tcol = s_temp + (32 * half) * kTempPitch + c;
-            int32_t* vcol = s_vu + (2 + 32 * half) * kVuPitch + c;
-            const int bg0 = I_k - R - 2 + 32 * half;  // global row of blurred output 0
+            const float* tcol = s_temp + (kRunV * half) * kTempPitch + c;
+            int32_t* vcol = s_vu + (2 + kRunV * half) * kVuPitch + c;
+            const int bg0 = I_k - R - 2 + kRunV * half;  // global row of blurred output 0
             // interior run: every blurred row has all 2R+1 taps inside the image, and every VU row has both vertical neighbours
             const bool y_interior = (bg0 - R >= 0) && (bg0 + kRunCol - 1 + R <= H - 1);
             int t0 = 0, t1 = 0;  // biased blurred values of rows o-2, o-1
@@ -513,8 +520,8 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
             // append this slab's kept pixels to the launch-wide list: every warp counts the bits of its 32 bitmap words and reserves
             // room with ONE global atomicAdd.  The atomic's round trip is hidden behind the next slab's row pass: the entries are
             // written by flush_pending() after it (and once more after the last slab).
-            pend_bits = s_bits[tid];
-            s_bits[tid] = 0;
+            pend_bits = 0;
+            if (tid < 4 * kSlab) { pend_bits = s_bits[tid]; s_bits[tid] = 0; }
             const int cnt = __popc(pend_bits);
             int incl = cnt;
 #pragma unroll
@@ -541,32 +548,32 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int R, bool USE_TMA, int DIV>
+template <int R, bool USE_TMA, int DIV, int SLAB>
 static int launch_one2(b200_ctx* ctx, cudaStream_t st, const FrontParams& p, const CUtensorMap& tmap, dim3 grid) {
-    const f2::SmemLayout L = f2::smem_layout(R);
+    const f2::SmemLayout L = f2::smem_layout(R, SLAB);
     static bool configured[64] = {false};  // per instantiation, per device
     if (!configured[ctx->device & 63]) {
-        CB_CUDA(cudaFuncSetAttribute(f2::front2_kernel<R, USE_TMA, DIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        CB_CUDA(cudaFuncSetAttribute(f2::front2_kernel<R, USE_TMA, DIV, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
         configured[ctx->device & 63] = true;
     }
     {
         ProfScope ps(ctx, st, 0);
-        f2::front2_kernel<R, USE_TMA, DIV><<<grid, f2::kThreads, L.total, st>>>(p, tmap);
+        f2::front2_kernel<R, USE_TMA, DIV, SLAB><<<grid, f2::kThreads, L.total, st>>>(p, tmap);
     }
     CB_CUDA(cudaGetLastError());
     ctx->launches++;
     return B200_OK;
 }
 
-template <int R>
+template <int R, int SLAB>
 static int launch_r2(b200_ctx* ctx, cudaStream_t st, const FrontParams& p, const CUtensorMap& tmap, dim3 grid, bool use_tma, int div) {
     if (use_tma) {
-        if (div == 1) return launch_one2<R, true, 1>(ctx, st, p, tmap, grid);
-        if (div == 3) return launch_one2<R, true, 3>(ctx, st, p, tmap, grid);
-        return launch_one2<R, true, 5>(ctx, st, p, tmap, grid);
+        if (div == 1) return launch_one2<R, true, 1, SLAB>(ctx, st, p, tmap, grid);
+        if (div == 3) return launch_one2<R, true, 3, SLAB>(ctx, st, p, tmap, grid);
+        return launch_one2<R, true, 5, SLAB>(ctx, st, p, tmap, grid);
     }
     // generic staging (odd widths) is not a throughput path: one instantiation, the always-valid division
-    return launch_one2<R, false, 5>(ctx, st, p, tmap, grid);
+    return launch_one2<R, false, 5, SLAB>(ctx, st, p, tmap, grid);
 }
 
 bool front2_supports(int radius) {
@@ -579,18 +586,18 @@ bool front2_supports(int radius) {
 // Bands per frame: every band pays 2R+4 warm-up rows and is processed in 64-row slabs, so pick the band count
 // that minimises (slabs per band) x (waves of CTAs) — enough CTAs to fill the machine, few enough that the
 // warm-up and the last partly-filled slab stay small.
-static int choose_bands2(const b200_ctx* ctx, int out_rows, int strips, int frames, int radius) {
-    const int slots = 2 * (ctx->sm_count > 0 ? ctx->sm_count : 148);
+static int choose_bands2(const b200_ctx* ctx, int out_rows, int strips, int frames, int radius, int slab) {
+    const int slots = (slab == 64 ? 2 : 4) * (ctx->sm_count > 0 ? ctx->sm_count : 148);
     const long long per_band = (long long)strips * frames;
     int best = 1;
     double best_cost = 1e300;
-    const int max_bands = out_rows / f2::kSlab > 0 ? out_rows / f2::kSlab : 1;
+    const int max_bands = out_rows / 64 > 0 ? out_rows / 64 : 1;
     for (int b = 1; b <= max_bands && b <= 64; ++b) {
         const int rows = (out_rows + b - 1) / b;
-        const int slabs = (rows + 2 * radius + 4 + f2::kSlab - 1) / f2::kSlab;
+        const int slabs = (rows + 2 * radius + 4 + slab - 1) / slab;
         const long long ctas = per_band * b;
         const long long waves = (ctas + slots - 1) / slots;
-        const double cost = (double)waves * slabs;  // time ~ waves x slabs per CTA
+        const double cost = (double)waves * slabs * slab;  // time ~ waves x rows marched per CTA
         if (cost < best_cost * 0.999) { best_cost = cost; best = b; }
     }
     return best;
@@ -601,20 +608,25 @@ int launch_front2(b200_ctx* ctx, cudaStream_t st, const FrontParams& p_in) {
     const int radius = p.radius;
     const int strips = (p.width + f2::kTW - 1) / f2::kTW;
     p.tiles_x = strips;
-    if (p.tiles_y <= 0) p.tiles_y = choose_bands2(ctx, p.out_rows, strips, p.n_frames, radius);
+    // 64-row slabs, 2 CTAs per SM.  The kernel also builds with 32-row slabs (4 CTAs per SM, 63 registers): measured 3.5 % slower
+    // on the 4K batch — twice the resident warps do not make up for the shorter runs' extra products and warm-up rows — so
+    // only the 64-row form is instantiated.
+    constexpr int slab = 64;
+    if (p.tiles_y <= 0) p.tiles_y = choose_bands2(ctx, p.out_rows, strips, p.n_frames, radius, slab);
     dim3 grid(strips, p.tiles_y, p.n_frames);
     CUtensorMap tmap;
     bool use_tma = false;
-    CB_TRY(make_input_tensor_map(p, f2::in_pitch_for(radius), f2::kSlab, &tmap, &use_tma));
+    CB_TRY(make_input_tensor_map(p, f2::in_pitch_for(radius), slab, &tmap, &use_tma));
     const int div3 = ctx->gauss.div_mode;
     p.div_c = ctx->gauss.div_c;
+
     switch (radius) {
-        case 2: return launch_r2<2>(ctx, st, p, tmap, grid, use_tma, div3);
-        case 3: return launch_r2<3>(ctx, st, p, tmap, grid, use_tma, div3);
-        case 5: return launch_r2<5>(ctx, st, p, tmap, grid, use_tma, div3);
-        case 6: return launch_r2<6>(ctx, st, p, tmap, grid, use_tma, div3);
-        case 9: return launch_r2<9>(ctx, st, p, tmap, grid, use_tma, div3);
-        case 15: return launch_r2<15>(ctx, st, p, tmap, grid, use_tma, div3);
+        case 2: return launch_r2<2, 64>(ctx, st, p, tmap, grid, use_tma, div3);
+        case 3: return launch_r2<3, 64>(ctx, st, p, tmap, grid, use_tma, div3);
+        case 5: return launch_r2<5, 64>(ctx, st, p, tmap, grid, use_tma, div3);
+        case 6: return launch_r2<6, 64>(ctx, st, p, tmap, grid, use_tma, div3);
+        case 9: return launch_r2<9, 64>(ctx, st, p, tmap, grid, use_tma, div3);
+        case 15: return launch_r2<15, 64>(ctx, st, p, tmap, grid, use_tma, div3);
         default: break;
     }
     set_error("front2 kernel not built for radius %d", radius);

@@ -554,6 +554,7 @@ static int launch_one2(b200_ctx* ctx, cudaStream_t st, const FrontParams& p, con
     static bool configured[64] = {false};  // per instantiation, per device
     if (!configured[ctx->device & 63]) {
         CB_CUDA(cudaFuncSetAttribute(f2::front2_kernel<R, USE_TMA, DIV, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        CB_CUDA(cudaFuncSetAttribute(f2::front2_kernel<R, USE_TMA, DIV, SLAB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured[ctx->device & 63] = true;
     }
     {
@@ -608,9 +609,9 @@ int launch_front2(b200_ctx* ctx, cudaStream_t st, const FrontParams& p_in) {
     const int radius = p.radius;
     const int strips = (p.width + f2::kTW - 1) / f2::kTW;
     p.tiles_x = strips;
-    // 64-row slabs, 2 CTAs per SM.  The kernel also builds with 32-row slabs (4 CTAs per SM, 63 registers): measured 3.5 % slower
-    // on the 4K batch — twice the resident warps do not make up for the shorter runs' extra products and warm-up rows — so
-    // only the 64-row form is instantiated.
+    // 64-row slabs, 2 CTAs per SM.  The kernel also builds with 32-row slabs (4 CTAs per SM, 63 registers; ncu: issue slots 74 %
+    // busy instead of 63 %) but then executes 19 % more instructions (shorter runs share fewer products, twice the tail copies and
+    // per-slab set-up) and ends up 2-3 % slower on the 4K batch, so only the 64-row form is instantiated.
     constexpr int slab = 64;
     if (p.tiles_y <= 0) p.tiles_y = choose_bands2(ctx, p.out_rows, strips, p.n_frames, radius, slab);
     dim3 grid(strips, p.tiles_y, p.n_frames);

@@ -615,11 +615,14 @@ int b200_canny_batch_host(b200_ctx* ctx, const uint8_t* frames, int n_frames, in
         }
     }
     if (packed && !ctx->pool) {
-        // measured on the 16-vCPU B200 hosts (tools/e2e_probe.py): 4 expanding threads (3 workers + the caller) keep up with the
-        // link; more of them only fight the DMA engine for host-memory bandwidth (e2e 52.7 Gpix/s with 4, 50 with 6-8, 45 with 10,
-        // 34 with 16)
+        // measured on the B200 hosts (tools/e2e_probe.py, tools/e2e_multi.sh): 4 expanding threads (3 workers + the caller) keep up
+        // with the link when one process owns the host (e2e 52.7 Gpix/s with 4, 50 with 6-8, 45 with 10, 34 with 16 threads: more
+        // of them only fight the DMA engine for host-memory bandwidth); with 8 processes on a 32-vCPU host 2 each are best
+        // (aggregate 131 Gpix/s against 87 with 4 and 104 with 1).  LOCAL_WORLD_SIZE is what torchrun exports.
         unsigned hc = std::thread::hardware_concurrency();
-        int n_threads = (int)std::min<unsigned>(std::max<unsigned>((hc ? hc : 4) / 2, 1), 4) - 1;
+        int local_world = 1;
+        if (const char* e = getenv("LOCAL_WORLD_SIZE")) local_world = std::max(1, atoi(e));
+        int n_threads = (int)std::min<unsigned>(std::max<unsigned>((hc ? hc : 4) / (2u * (unsigned)local_world), 1), 4) - 1;
         if (const char* e = getenv("B200_CANNY_UNPACK_THREADS")) n_threads = std::max(0, atoi(e) - 1);
         ctx->pool = new UnpackPool(std::max(0, n_threads));
     }

@@ -381,8 +381,8 @@ def run_bands(a, rank, world, local_rank):
     H, W = a.band_height, a.band_width
     pipe = sharded.BandPipeline(ctx, H, W, rank, world, a.sigma, LO, HI)
     g = pipe.geo
-    band = torch.empty((g.rows, W), dtype=torch.uint8, device="cuda")
-    edges = torch.empty_like(band)
+    band = pipe.band_view()   # the rank's rows live inside the pipeline's persistent halo buffer: no per-step copy
+    edges = torch.empty((g.rows, W), dtype=torch.uint8, device="cuda")
     check(lib.b200_synth_rows_device(ctx.handle, band.data_ptr(), g.row0, g.rows, W, a.kind, 1234, 0))
     torch.cuda.synchronize()
 
@@ -392,7 +392,12 @@ def run_bands(a, rank, world, local_rank):
         torch.cuda.synchronize()
 
     for _ in range(a.warmup):
-        pipe.run(band, edges)
+        pipe.run(None, edges)
+    barrier()
+    pipe.timings = {}
+    pipe.run(None, edges)         # one untimed step with per-stage events (reported as config.stage_ms)
+    stage_ms = {k: round(v, 3) for k, v in pipe.timings.items()}
+    pipe.timings = None
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -400,7 +405,7 @@ def run_bands(a, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
-        pipe.run(band, edges)
+        pipe.run(None, edges)
     e1.record()
     barrier()
     clocks = sampler.stop()
@@ -427,7 +432,7 @@ def run_bands(a, rank, world, local_rank):
                                    "(BASELINE configs[4])", "height": H, "width": W, "sigma": a.sigma, "bands": world,
                        "band_rows": g.rows, "halo_rows": g.halo, "halo_bytes_per_interior_rank_per_step": halo_bytes,
                        "record_bytes_all_gathered_per_step": world * pipe.n_records * 8,
-                       "generator": ["shapes", "noise", "const"][a.kind],
+                       "generator": ["shapes", "noise", "const"][a.kind], "stage_ms_rank0": stage_ms,
                        "l2": "band (%.2f GB per GPU) exceeds the 126 MB L2" % (g.rows * W / 1e9)},
             "clocks": clocks, "gpu_launches": int(launches), "edge_fraction": round(float(tot.item()) / px, 6),
             "roofline": {"bound": "hbm", "kernel": "whole band pipeline", "achieved": round(value * 1e6 * ALG_BYTES_PER_PX / 1e9 / world, 2),

@@ -120,7 +120,11 @@ def gather_records(records, world: int, group=None):
 # band pipeline on one rank
 # ---------------------------------------------------------------------------------------------------
 class BandPipeline:
-    """Canny of one row band of a larger image on this rank's GPU."""
+    """Canny of one row band of a larger image on this rank's GPU.
+
+    The pipeline owns ONE persistent device buffer [halo above | band | halo below] (`buffer`), so a step neither allocates nor
+    copies the band: callers that produce their rows on the device write them straight into `band_view()`; `run(band)` with an
+    external tensor copies it in first."""
 
     def __init__(self, ctx: Context, height: int, width: int, rank: int, world: int, sigma: float, min_val: int,
                  max_val: int, group=None):
@@ -129,6 +133,47 @@ class BandPipeline:
         self.geo = band_geometry(height, width, rank, world, sigma)
         self.lib = load()
         self.n_records = int(self.lib.b200_band_record_count(width))
+        self.buffer = None      # (buffer_rows, W) uint8
+        self.records = None     # this band's boundary records (bytes)
+        self.all_records = None
+        self.timings = None     # set to a dict to collect per-stage CUDA-event times (ms) of the next run()
+
+    # ---- persistent device state -------------------------------------------------------------------------------
+    def _ensure(self, device):
+        import torch
+
+        g = self.geo
+        if self.buffer is None or self.buffer.device != device:
+            self.buffer = torch.empty((g.buffer_rows, g.width), dtype=torch.uint8, device=device)
+            self.records = torch.empty((self.n_records * RECORD_BYTES,), dtype=torch.uint8, device=device)
+            self.all_records = torch.empty((g.world * self.n_records * RECORD_BYTES,), dtype=torch.uint8, device=device)
+
+    def band_view(self, device=None):
+        """The (rows, W) window of the persistent buffer that holds this rank's own rows."""
+        import torch
+
+        self._ensure(torch.device("cuda", self.ctx.device) if device is None else device)
+        g = self.geo
+        return self.buffer[g.halo_above:g.halo_above + g.rows]
+
+    # ---- the two exchange steps, in place ----------------------------------------------------------------------
+    def exchange_halos_inplace(self):
+        """Fills the halo rows of the persistent buffer from the neighbours' edge rows (one batched NCCL send/recv round)."""
+        import torch.distributed as dist
+
+        g = self.geo
+        if g.world == 1:
+            return
+        buf, a = self.buffer, g.halo_above
+        ops = []
+        if g.rank > 0:
+            ops.append(dist.P2POp(dist.isend, buf[a:a + g.halo], g.rank - 1, self.group))
+            ops.append(dist.P2POp(dist.irecv, buf[:a], g.rank - 1, self.group))
+        if g.rank + 1 < g.world:
+            ops.append(dist.P2POp(dist.isend, buf[a + g.rows - g.halo:a + g.rows], g.rank + 1, self.group))
+            ops.append(dist.P2POp(dist.irecv, buf[a + g.rows:], g.rank + 1, self.group))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
 
     def front(self, buf, edges) -> None:
         g = self.geo
@@ -142,22 +187,49 @@ class BandPipeline:
         g = self.geo
         check(self.lib.b200_band_finalize(self.ctx.handle, all_records.data_ptr(), g.world, g.rank, g.rows, g.width, edges.data_ptr()))
 
-    def run(self, band, edges=None):
-        """band: (rows, W) uint8 CUDA tensor (this rank's rows).  Returns the (rows, W) uint8 0/255 edge band.
-        Work is issued on torch's current stream (the context is pointed at it), so NCCL ordering is the
-        stream's ordering."""
+    def run(self, band=None, edges=None):
+        """band: (rows, W) uint8 CUDA tensor with this rank's rows, or None when they were written into band_view().
+        Returns the (rows, W) uint8 0/255 edge band.  Work is issued on torch's current stream (the context is pointed at it), so
+        NCCL ordering is the stream's ordering."""
         import torch
+        import torch.distributed as dist
 
         g = self.geo
+        dev = band.device if band is not None else torch.device("cuda", self.ctx.device)
+        self._ensure(dev)
         self.ctx.set_stream(torch.cuda.current_stream().cuda_stream)
         if edges is None:
-            edges = torch.empty((g.rows, g.width), dtype=torch.uint8, device=band.device)
-        buf = exchange_halos(band, g, self.group)
-        self.front(buf, edges)
-        records = torch.empty((self.n_records * RECORD_BYTES,), dtype=torch.uint8, device=band.device)
-        self.export(records)
-        all_records = gather_records(records, g.world, self.group)
-        self.finalize(all_records, edges)
+            edges = torch.empty((g.rows, g.width), dtype=torch.uint8, device=dev)
+        marks = []
+
+        def mark(name):
+            if self.timings is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((name, e))
+
+        mark("start")
+        if band is not None and band.data_ptr() != self.band_view().data_ptr():
+            self.band_view().copy_(band)
+        mark("copy_in")
+        self.exchange_halos_inplace()
+        mark("halo_exchange")
+        self.front(self.buffer, edges)
+        mark("front+label")
+        self.export(self.records)
+        mark("export")
+        if g.world > 1:
+            dist.all_gather_into_tensor(self.all_records, self.records, group=self.group)
+            allrec = self.all_records
+        else:
+            allrec = self.records
+        mark("all_gather")
+        self.finalize(allrec, edges)
+        mark("finalize")
+        if self.timings is not None:
+            torch.cuda.synchronize()
+            for (_, e0), (name, e1) in zip(marks, marks[1:]):
+                self.timings[name] = self.timings.get(name, 0.0) + e0.elapsed_time(e1)
         return edges
 
 

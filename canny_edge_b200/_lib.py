@@ -60,8 +60,6 @@ SIGNATURES = {
     "b200_band_halo_rows": (C.c_int, [C.c_float]),
     "b200_band_record_count": (C.c_int, [C.c_int]),
     "b200_band_front": (C.c_int, [_ctx, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _u8p]),
-    "b200_band_front_interior": (C.c_int, [_ctx, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _u8p]),
-    "b200_band_front_edges": (C.c_int, [_ctx, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _u8p]),
     "b200_band_boundary_export": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_void_p]),
     "b200_band_finalize": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]),
     "b200_synth_host": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int]),

@@ -241,7 +241,7 @@ static int run_frames_device(b200_ctx* ctx, cudaStream_t st, int slot, const uin
     FrontParams fp;
     memset(&fp, 0, sizeof(fp));
     fp.in = d_in; fp.in_frame_stride = px; fp.in_row0 = 0; fp.in_rows = h; fp.width = w; fp.height = h;
-    fp.out_row0 = 0; fp.out_rows = h; fp.plane_row0 = 0; fp.n_frames = nf; fp.cls = d_out; fp.out_frame_stride = px;
+    fp.out_row0 = 0; fp.out_rows = h; fp.n_frames = nf; fp.cls = d_out; fp.out_frame_stride = px;
     fp.blur = blur; fp.mag = mag; fp.ang = ang; fp.nms = nms;
     fp.w = ctx->gauss.d_w; fp.count = ctx->gauss.d_count; fp.radius = ctx->gauss.radius;
     fill_thresholds(fp, lo, hi);

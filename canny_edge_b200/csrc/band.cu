@@ -122,11 +122,8 @@ extern "C" {
 int b200_band_halo_rows(float sigma) { return host_window(sigma) / 2 + 2; }
 int b200_band_record_count(int width) { return band_records(width); }
 
-// Stages 1-3 of a band in up to three front-kernel launches that fill ONE class plane: the interior rows, which read no halo
-// row (so they can run while the halo exchange is still in flight), and the two edge stripes of window/2+2 rows, which do.
-static int band_front_impl(b200_ctx* ctx, const uint8_t* d_rows, int halo_above, int halo_below, int band_rows, int row0,
-                           int global_height, int width, float sigma, int lo, int hi, uint8_t* d_edges, bool do_interior,
-                           bool do_edges) {
+int b200_band_front(b200_ctx* ctx, const uint8_t* d_rows, int halo_above, int halo_below, int band_rows, int row0,
+                    int global_height, int width, float sigma, int lo, int hi, uint8_t* d_edges) {
     if (!d_rows || !d_edges) { set_error("null pointer"); return B200_ERR_INVALID_ARG; }
     if (band_rows < 2 || width < 2 || global_height < 2 || row0 < 0 || row0 + band_rows > global_height || halo_above < 0 ||
         halo_below < 0 || halo_above > row0 || row0 + band_rows + halo_below > global_height) {
@@ -157,7 +154,7 @@ static int band_front_impl(b200_ctx* ctx, const uint8_t* d_rows, int halo_above,
     fp.in_row0 = row0 - halo_above;
     fp.in_rows = halo_above + band_rows + halo_below;
     fp.width = width; fp.height = global_height;
-    fp.plane_row0 = row0; fp.n_frames = 1;
+    fp.out_row0 = row0; fp.out_rows = band_rows; fp.n_frames = 1;
     fp.cls = d_edges; fp.out_frame_stride = px;
     fp.w = ctx->gauss.d_w; fp.count = ctx->gauss.d_count; fp.radius = ctx->gauss.radius;
     {
@@ -169,60 +166,25 @@ static int band_front_impl(b200_ctx* ctx, const uint8_t* d_rows, int halo_above,
     fp.parent = reinterpret_cast<int32_t*>(ctx->ws_band_parent.ptr);
     fp.kept_count = reinterpret_cast<unsigned int*>(ctx->ws_band_list.ptr);
     fp.kept_list = reinterpret_cast<uint32_t*>(ctx->ws_band_list.ptr) + 16;
-    // stripes only when both they and an interior exist; a band too short for that is done in one launch with the edges
-    const bool split = (need_above > 0 || need_below > 0) && band_rows - need_above - need_below >= 2;
+    CB_CUDA(cudaMemsetAsync(fp.kept_count, 0, sizeof(unsigned int), st));
     bool sparse = false;
-    if (do_interior) {
-        CB_CUDA(cudaMemsetAsync(fp.kept_count, 0, sizeof(unsigned int), st));
-        if (split || (need_above == 0 && need_below == 0)) {
-            fp.out_row0 = row0 + (split ? need_above : 0);
-            fp.out_rows = band_rows - (split ? need_above + need_below : 0);
-            CB_TRY(launch_front(ctx, st, fp, &sparse));
-            ctx->band_sparse = sparse;
-        }
+    CB_TRY(launch_front(ctx, st, fp, &sparse));
+    const bool dense = ctx->kept_px[3] > 0 && (long long)ctx->h_kept[3] * 8 > ctx->kept_px[3];   // previous band on this context
+    if (sparse) {
+        CB_CUDA(cudaMemcpyAsync(&ctx->h_kept[3], fp.kept_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        ctx->kept_px[3] = px;
     }
-    if (do_edges) {
-        if (split) {
-            fp.tiles_y = 1;
-            if (need_above > 0) { fp.out_row0 = row0; fp.out_rows = need_above; CB_TRY(launch_front(ctx, st, fp, &sparse)); }
-            if (need_below > 0) { fp.out_row0 = row0 + band_rows - need_below; fp.out_rows = need_below; CB_TRY(launch_front(ctx, st, fp, &sparse)); }
-            fp.tiles_y = 0;
-        } else if (need_above > 0 || need_below > 0) {
-            fp.out_row0 = row0; fp.out_rows = band_rows;
-            CB_TRY(launch_front(ctx, st, fp, &sparse));
-        } else {
-            sparse = ctx->band_sparse;   // everything was produced by the interior launch
-        }
-        const bool dense = ctx->kept_px[3] > 0 && (long long)ctx->h_kept[3] * 8 > ctx->kept_px[3];   // previous band on this context
-        if (sparse) {
-            CB_CUDA(cudaMemcpyAsync(&ctx->h_kept[3], fp.kept_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-            ctx->kept_px[3] = px;
-        }
-        sparse = sparse && !dense;
-        ctx->band_sparse = sparse;
-        HystParams hp;
-        memset(&hp, 0, sizeof(hp));
-        hp.list = sparse ? fp.kept_list : nullptr;
-        hp.count = fp.kept_count;
-        hp.cls = d_edges; hp.parent = reinterpret_cast<int32_t*>(ctx->ws_band_parent.ptr);
-        hp.frame_stride = px; hp.rows = band_rows; hp.width = width; hp.row0 = row0; hp.n_frames = 1;
-        CB_TRY(launch_ccl_label(ctx, st, hp));
-        ctx->band_rows = band_rows; ctx->band_width = width; ctx->band_row0 = row0; ctx->band_cls = d_edges;
-    }
+    sparse = sparse && !dense;
+    ctx->band_sparse = sparse;
+    HystParams hp;
+    memset(&hp, 0, sizeof(hp));
+    hp.list = sparse ? fp.kept_list : nullptr;
+    hp.count = fp.kept_count;
+    hp.cls = d_edges; hp.parent = reinterpret_cast<int32_t*>(ctx->ws_band_parent.ptr);
+    hp.frame_stride = px; hp.rows = band_rows; hp.width = width; hp.row0 = row0; hp.n_frames = 1;
+    CB_TRY(launch_ccl_label(ctx, st, hp));
+    ctx->band_rows = band_rows; ctx->band_width = width; ctx->band_row0 = row0; ctx->band_cls = d_edges;
     return B200_OK;
-}
-
-int b200_band_front(b200_ctx* ctx, const uint8_t* d_rows, int halo_above, int halo_below, int band_rows, int row0,
-                    int global_height, int width, float sigma, int lo, int hi, uint8_t* d_edges) {
-    return band_front_impl(ctx, d_rows, halo_above, halo_below, band_rows, row0, global_height, width, sigma, lo, hi, d_edges, true, true);
-}
-int b200_band_front_interior(b200_ctx* ctx, const uint8_t* d_rows, int halo_above, int halo_below, int band_rows, int row0,
-                             int global_height, int width, float sigma, int lo, int hi, uint8_t* d_edges) {
-    return band_front_impl(ctx, d_rows, halo_above, halo_below, band_rows, row0, global_height, width, sigma, lo, hi, d_edges, true, false);
-}
-int b200_band_front_edges(b200_ctx* ctx, const uint8_t* d_rows, int halo_above, int halo_below, int band_rows, int row0,
-                          int global_height, int width, float sigma, int lo, int hi, uint8_t* d_edges) {
-    return band_front_impl(ctx, d_rows, halo_above, halo_below, band_rows, row0, global_height, width, sigma, lo, hi, d_edges, false, true);
 }
 
 int b200_band_boundary_export(b200_ctx* ctx, int band_rows, int width, b200_band_record* d_records) {

@@ -56,8 +56,7 @@ struct FrontParams {
     int width;              // image width == pitch of every plane
     int height;             // GLOBAL image height (border rules key off this)
     int out_row0;           // first global row this launch produces
-    int out_rows;           // number of rows produced
-    int plane_row0;         // global row of row 0 of every output plane (== out_row0 unless a plane is filled by several launches)
+    int out_rows;           // number of rows produced (planes below are indexed from out_row0)
     int n_frames;
     uint8_t* cls;           // out: class map (0 / 1 weak / 255 strong), out_rows*width per frame
     long long out_frame_stride;  // elements between frames in every output plane

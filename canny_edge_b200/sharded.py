@@ -157,15 +157,13 @@ class BandPipeline:
         return self.buffer[g.halo_above:g.halo_above + g.rows]
 
     # ---- the two exchange steps, in place ----------------------------------------------------------------------
-    def exchange_halos_inplace(self, wait: bool = True):
-        """Fills the halo rows of the persistent buffer from the neighbours' edge rows (one batched NCCL send/recv round).
-        wait=False returns the outstanding requests instead of waiting: NCCL runs them on its own stream, so kernels issued on
-        the current stream meanwhile overlap the exchange; req.wait() later makes the current stream wait for the halos."""
+    def exchange_halos_inplace(self):
+        """Fills the halo rows of the persistent buffer from the neighbours' edge rows (one batched NCCL send/recv round)."""
         import torch.distributed as dist
 
         g = self.geo
         if g.world == 1:
-            return []
+            return
         buf, a = self.buffer, g.halo_above
         ops = []
         if g.rank > 0:
@@ -174,17 +172,8 @@ class BandPipeline:
         if g.rank + 1 < g.world:
             ops.append(dist.P2POp(dist.isend, buf[a + g.rows - g.halo:a + g.rows], g.rank + 1, self.group))
             ops.append(dist.P2POp(dist.irecv, buf[a + g.rows:], g.rank + 1, self.group))
-        reqs = dist.batch_isend_irecv(ops)
-        if wait:
-            for req in reqs:
-                req.wait()
-            return []
-        return reqs
-
-    def _front_call(self, fn, buf, edges) -> None:
-        g = self.geo
-        check(fn(self.ctx.handle, buf.data_ptr(), g.halo_above, g.halo_below, g.rows, g.row0, g.height, g.width,
-                 C.c_float(self.sigma), self.lo, self.hi, edges.data_ptr()))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
 
     def front(self, buf, edges) -> None:
         g = self.geo
@@ -223,14 +212,10 @@ class BandPipeline:
         if band is not None and band.data_ptr() != self.band_view().data_ptr():
             self.band_view().copy_(band)
         mark("copy_in")
-        # the halo exchange runs on NCCL's stream while the interior of the band (which reads no halo row) is processed here
-        reqs = self.exchange_halos_inplace(wait=False)
-        self._front_call(self.lib.b200_band_front_interior, self.buffer, edges)
-        mark("front_interior")
-        for req in reqs:
-            req.wait()
-        self._front_call(self.lib.b200_band_front_edges, self.buffer, edges)
-        mark("front_edges+label")
+        self.exchange_halos_inplace()
+        mark("halo_exchange")
+        self.front(self.buffer, edges)
+        mark("front+label")
         self.export(self.records)
         mark("export")
         if g.world > 1:

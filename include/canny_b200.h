@@ -198,15 +198,6 @@ int b200_band_halo_rows(float sigma);
 int b200_band_front(b200_ctx* ctx, const uint8_t* d_rows, int halo_above, int halo_below,
                     int band_rows, int row0, int global_height, int width, float sigma, int min_val,
                     int max_val, uint8_t* d_edges);
-/* The same work as b200_band_front in two calls, so the halo exchange can overlap the bulk of the band:
- *   b200_band_front_interior  rows whose stencils stay inside the band (all but the first / last window/2+2 rows): reads NO halo
- *                             row, so it may be issued while the halos are still in flight;
- *   b200_band_front_edges     the two edge stripes (they read the halos) + the band-local connected components.
- * Same arguments as b200_band_front; _interior then _edges on the same stream is exactly b200_band_front. */
-int b200_band_front_interior(b200_ctx* ctx, const uint8_t* d_rows, int halo_above, int halo_below, int band_rows, int row0,
-                             int global_height, int width, float sigma, int min_val, int max_val, uint8_t* d_edges);
-int b200_band_front_edges(b200_ctx* ctx, const uint8_t* d_rows, int halo_above, int halo_below, int band_rows, int row0,
-                          int global_height, int width, float sigma, int min_val, int max_val, uint8_t* d_edges);
 int b200_band_boundary_export(b200_ctx* ctx, int band_rows, int width, b200_band_record* d_records);
 int b200_band_finalize(b200_ctx* ctx, const b200_band_record* d_all_records, int n_bands,
                        int band_index, int band_rows, int width, uint8_t* d_edges);

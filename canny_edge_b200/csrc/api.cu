@@ -249,7 +249,7 @@ static int run_frames_device(b200_ctx* ctx, cudaStream_t st, int slot, const uin
     fp.parent = reinterpret_cast<int32_t*>(ctx->ws_parent[slot].ptr);
     fp.kept_count = reinterpret_cast<unsigned int*>(ctx->ws_list[slot].ptr);
     fp.kept_list = reinterpret_cast<uint32_t*>(ctx->ws_list[slot].ptr) + 16;
-    CB_CUDA(cudaMemsetAsync(fp.kept_count, 0, sizeof(unsigned int), st));
+    CB_CUDA(cudaMemsetAsync(fp.kept_count, 0, 2 * sizeof(unsigned int), st));   // list length + link-kernel block counter
     bool sparse = false;
     CB_TRY(launch_front(ctx, st, fp, &sparse));
     const bool dense = ctx->kept_px[slot] > 0 && (long long)ctx->h_kept[slot] * 8 > ctx->kept_px[slot];   // previous launch of this slot
@@ -262,6 +262,7 @@ static int run_frames_device(b200_ctx* ctx, cudaStream_t st, int slot, const uin
     hp.cls = d_out;
     hp.list = (sparse && !dense) ? fp.kept_list : nullptr;
     hp.count = fp.kept_count;
+    hp.done = fp.kept_count + 1;
     hp.parent = reinterpret_cast<int32_t*>(ctx->ws_parent[slot].ptr);
     hp.frame_stride = px; hp.rows = h; hp.width = w; hp.row0 = 0; hp.n_frames = nf;
     CB_TRY(launch_hysteresis(ctx, st, hp));

@@ -42,7 +42,11 @@ __global__ void band_roots_kernel(const uint8_t* __restrict__ cls, const int32_t
     if (i >= band_records(W)) return;
     const int px = record_pixel(i, rows, W, row0);
     int r = kNone;
-    if (px >= 0 && cls[px] != 0) r = g_find(parent, px);
+    if (px >= 0) {
+        const int c = cls[px];
+        if (c == 255) r = kSuper;                 // strong pixels are final (the list-driven path gives them no union-find slot)
+        else if (c != 0) r = g_find(parent, px);
+    }
     roots[i] = r;
 }
 // pass 2: every non-strong root is claimed by ONE of the records that reach it (the largest index wins)
@@ -166,7 +170,7 @@ int b200_band_front(b200_ctx* ctx, const uint8_t* d_rows, int halo_above, int ha
     fp.parent = reinterpret_cast<int32_t*>(ctx->ws_band_parent.ptr);
     fp.kept_count = reinterpret_cast<unsigned int*>(ctx->ws_band_list.ptr);
     fp.kept_list = reinterpret_cast<uint32_t*>(ctx->ws_band_list.ptr) + 16;
-    CB_CUDA(cudaMemsetAsync(fp.kept_count, 0, sizeof(unsigned int), st));
+    CB_CUDA(cudaMemsetAsync(fp.kept_count, 0, 2 * sizeof(unsigned int), st));   // list length + link-kernel block counter
     bool sparse = false;
     CB_TRY(launch_front(ctx, st, fp, &sparse));
     const bool dense = ctx->kept_px[3] > 0 && (long long)ctx->h_kept[3] * 8 > ctx->kept_px[3];   // previous band on this context
@@ -180,6 +184,7 @@ int b200_band_front(b200_ctx* ctx, const uint8_t* d_rows, int halo_above, int ha
     memset(&hp, 0, sizeof(hp));
     hp.list = sparse ? fp.kept_list : nullptr;
     hp.count = fp.kept_count;
+    hp.done = fp.kept_count + 1;
     hp.cls = d_edges; hp.parent = reinterpret_cast<int32_t*>(ctx->ws_band_parent.ptr);
     hp.frame_stride = px; hp.rows = band_rows; hp.width = width; hp.row0 = row0; hp.n_frames = 1;
     CB_TRY(launch_ccl_label(ctx, st, hp));
@@ -253,6 +258,7 @@ int b200_band_finalize(b200_ctx* ctx, const b200_band_record* d_all, int n_bands
     hp.cls = d_edges; hp.parent = parent;
     hp.list = ctx->band_sparse ? reinterpret_cast<const uint32_t*>(ctx->ws_band_list.ptr) + 16 : nullptr;
     hp.count = reinterpret_cast<const unsigned int*>(ctx->ws_band_list.ptr);
+    hp.done = reinterpret_cast<unsigned int*>(ctx->ws_band_list.ptr) + 1;
     hp.frame_stride = (long long)band_rows * width; hp.rows = band_rows; hp.width = width; hp.row0 = ctx->band_row0; hp.n_frames = 1;
     CB_TRY(launch_ccl_resolve(ctx, st, hp));
     return B200_OK;

@@ -116,7 +116,7 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
     const uint32_t bar0 = smem_u32(smem + L.bar_off);
     uint16_t* s_ent = reinterpret_cast<uint16_t*>(smem + L.ent_off);
     uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem + L.bits_off);
-    const bool sparse = p.kept_list != nullptr;                  // uniform: also fill parent[] and the kept-pixel list
+    const bool sparse = p.kept_list != nullptr;                  // uniform: also fill parent[] and the weak-pixel list
     int32_t* s_np = reinterpret_cast<int32_t*>(s_temp + T0 * kTempPitch);   // n-plane: the temp rows phase 1 refills next slab
 
     const int tid = threadIdx.x;
@@ -501,12 +501,13 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
                         if (na[e] < m2 && nb[e] < m2) {
                             const bool strong = n >= p.hi2;
                             orow[e] = strong ? (uint8_t)255 : (uint8_t)1;
-                            if (sparse) {
-                                // hand-over to the sparse hysteresis kernels: the pixel's union-find slot (itself, or the virtual
-                                // root SUPER = -1 of every strong component) and its bit in the slab's kept-pixel bitmap, from which
-                                // the list entries are made once the slab is finished
+                            if (sparse && !strong) {
+                                // hand-over to the list-driven hysteresis kernels: only WEAK pixels need any work there (a strong
+                                // pixel is final; its neighbours find it through the class map).  The weak pixel gets its union-
+                                // find slot (itself) and a bit in the slab's bitmap, from which the list entries are made once
+                                // the slab is finished
                                 const int rel = rr * W + 4 * el + e;
-                                par_base[rel] = strong ? -1 : idx_base + rel;
+                                par_base[rel] = idx_base + rel;
                                 const int col = 4 * el + e - 1;               // class column within the strip: j - 2
                                 atomicOr(&s_bits[rr * 4 + (col >> 5)], 1u << (col & 31));
                             }
@@ -517,7 +518,7 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
         }
         __syncthreads();  // (C) VU, n-plane and list reads done; the slab's kept-pixel bitmap is complete
         if (sparse) {
-            // append this slab's kept pixels to the launch-wide list: every warp counts the bits of its 32 bitmap words and reserves
+            // append this slab's weak pixels to the launch-wide list: every warp counts the bits of its 32 bitmap words and reserves
             // room with ONE global atomicAdd.  The atomic's round trip is hidden behind the next slab's row pass: the entries are
             // written by flush_pending() after it (and once more after the last slab).
             pend_bits = 0;

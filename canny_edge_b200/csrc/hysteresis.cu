@@ -250,23 +250,14 @@ ccl_final_kernel(const HystParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// sparse variants: driven by the kept-pixel list front2.cu writes (work ~ number of kept pixels, not pixels)
+// sparse variants: driven by the weak-pixel list front2.cu writes (work ~ number of weak pixels, not pixels)
 // ---------------------------------------------------------------------------------------------
-// front2 has already initialised parent[] for every kept pixel (its own launch-relative index; SUPER for strong pixels).  One
-// thread per kept pixel: it looks at its "forward" neighbours E, S (or SW / SE when S is not kept: with S kept the two diagonals
-// reach the pixel through S's own E links), so every undirected neighbour pair is visited exactly once, from its earlier endpoint
-// in raster order.  Two strong pixels already share the root SUPER; a strong and a weak one only need the weak one's component
-// hung under SUPER; only weak-weak pairs are real unions.  The pair (0,1)-(1,0) of the GLOBAL image is skipped (see the file header).
-__device__ __forceinline__ void sparse_link(int32_t* parent, int a, int ca, int b, int cb) {
-    if (ca == 255) {
-        if (cb != 255) g_union_halve(parent, b, kSuper);
-    } else if (cb == 255) {
-        g_union_halve(parent, a, kSuper);
-    } else {
-        g_union_halve(parent, a, b);
-    }
-}
-
+// Only weak pixels (class 1) need anything: a strong pixel is final.  front2 has initialised parent[] of every weak pixel to its
+// own launch-relative index.  One thread per weak pixel: the eight neighbours' class bytes are fetched together; any strong
+// neighbour hangs the pixel's component under SUPER; weak "forward" neighbours E, S (or SW / SE when S is not weak: with S weak
+// the two diagonals reach the pixel through S's own links) are united with it, so every weak-weak pair is visited exactly once,
+// from its earlier endpoint in raster order.  The pair (0,1)-(1,0) of the GLOBAL image is skipped in both directions (see the
+// file header): the one-way link is applied in the resolve kernel.
 __global__ void __launch_bounds__(256)
 ccl_sparse_link_kernel(const HystParams p) {
     const unsigned int n = *p.count;
@@ -277,46 +268,56 @@ ccl_sparse_link_kernel(const HystParams p) {
         const unsigned int rel = g % fs;
         const int y = (int)(rel / (unsigned int)W), x = (int)(rel - (unsigned int)y * (unsigned int)W);
         const uint8_t* c = p.cls + g;
-        // the four forward neighbours' class bytes are fetched together (one round trip to L2 instead of up to three dependent
-        // ones); neighbours outside the image count as "not kept"
-        const bool has_e = x + 1 < W, has_s = y + 1 < Hh, has_w = x > 0;
-        const int ca = c[0];
-        const int ce = has_e ? c[1] : 0;
-        const int cs = has_s ? c[W] : 0;
-        const bool quirk = (p.row0 + y == 0) && (x == 1);   // (0,1) -> its SW neighbour (1,0)
-        const int cw = (has_s && has_w && !quirk) ? c[W - 1] : 0;
-        const int cx = (has_s && has_e) ? c[W + 1] : 0;
-        if (ce) sparse_link(p.parent, (int)g, ca, (int)g + 1, ce);
-        if (cs) {
-            sparse_link(p.parent, (int)g, ca, (int)g + W, cs);
+        const bool has_n = y > 0, has_s = y + 1 < Hh, has_w = x > 0, has_e = x + 1 < W;
+        const bool top_rows = (p.row0 + y) <= 1;
+        const bool q01 = top_rows && (p.row0 + y == 0) && (x == 1);   // this pixel is (0,1): its SW neighbour (1,0) is off limits
+        const bool q10 = top_rows && (p.row0 + y == 1) && (x == 0);   // this pixel is (1,0): its NE neighbour (0,1) is off limits
+        const int c_nw = (has_n && has_w) ? c[-W - 1] : 0;
+        const int c_n = has_n ? c[-W] : 0;
+        const int c_ne = (has_n && has_e && !q10) ? c[-W + 1] : 0;
+        const int c_w = has_w ? c[-1] : 0;
+        const int c_e = has_e ? c[1] : 0;
+        const int c_sw = (has_s && has_w && !q01) ? c[W - 1] : 0;
+        const int c_s = has_s ? c[W] : 0;
+        const int c_se = (has_s && has_e) ? c[W + 1] : 0;
+        // classes are 0, 1 or 255: a strong neighbour anywhere around makes the component strong
+        if (((c_nw | c_n | c_ne | c_w | c_e | c_sw | c_s | c_se) & 0x80) != 0) g_union_halve(p.parent, (int)g, kSuper);
+        if (c_e == 1) g_union_halve(p.parent, (int)g, (int)g + 1);
+        if (c_s == 1) {
+            g_union_halve(p.parent, (int)g, (int)g + W);
         } else {
-            if (cw) sparse_link(p.parent, (int)g, ca, (int)g + W - 1, cw);
-            if (cx) sparse_link(p.parent, (int)g, ca, (int)g + W + 1, cx);
+            if (c_sw == 1) g_union_halve(p.parent, (int)g, (int)g + W - 1);
+            if (c_se == 1) g_union_halve(p.parent, (int)g, (int)g + W + 1);
         }
+    }
+    // The reference's one-way link (0,1) -> (1,0) (src/utils.cpp:399): once EVERY block has finished its unions the forest is
+    // final, and the last block to get here hangs (1,0)'s component under SUPER when (0,1) is strong or strong-connected.  The
+    // class bytes are still untouched at this point (the resolve kernel runs after this one).
+    if (p.row0 != 0 || Hh < 2 || W < 2) return;
+    __shared__ bool s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(p.done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int f = threadIdx.x; f < p.n_frames; f += blockDim.x) {
+        const unsigned int f0 = (unsigned int)f * fs;
+        const int c01 = p.cls[f0 + 1], c10 = p.cls[f0 + W];
+        if (c10 == 1 && (c01 == 255 || (c01 == 1 && g_find_halve(p.parent, (int)f0 + 1) == kSuper)))
+            g_union_halve(p.parent, (int)f0 + W, kSuper);
     }
 }
 
-// every kept WEAK pixel chases its root: 255 when the component hangs under SUPER (or is the target of the one-way link), else 0
+// every weak pixel chases its root: 255 when the component hangs under SUPER, else 0
 __global__ void __launch_bounds__(256)
 ccl_sparse_resolve_kernel(const HystParams p) {
     const unsigned int n = *p.count;
-    const int W = p.width, Hh = p.rows;
-    const unsigned int fs = (unsigned int)p.frame_stride;
-    const bool q_possible = (p.row0 == 0 && Hh >= 2 && W >= 2);
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const unsigned int g = p.list[i];
-        if (p.cls[g] != 1) continue;
-        const int root = g_find_halve(p.parent, (int)g);
-        bool on = (root == kSuper);
-        if (!on && q_possible) {
-            // the one-way link (0,1) -> (1,0) of the global image: if (0,1)'s component is strong, (1,0)'s becomes strong.  Reading
-            // the two class bytes while this kernel rewrites weak ones is benign: a byte only ever turns 0 when its component is
-            // neither strong nor the link's target, in which case the link does not apply anyway.
-            const unsigned int f0 = g - g % fs;
-            if (p.cls[f0 + 1] != 0 && p.cls[f0 + W] != 0 && g_find_halve(p.parent, (int)f0 + 1) == kSuper)
-                on = (root == g_find_halve(p.parent, (int)f0 + W));
-        }
-        p.cls[g] = on ? 255 : 0;
+        p.cls[g] = (g_find_halve(p.parent, (int)g) == kSuper) ? 255 : 0;
     }
 }
 

@@ -74,9 +74,9 @@ struct FrontParams {
     int ieee_div;           // 1: weights so small that sums can fall below 2^-100 -> use IEEE division instead of div_exact
     int tiles_x, tiles_y;
     // sparse hand-over to the hysteresis kernels (front2.cu only; both null -> not produced):
-    int32_t* parent;        // union-find slots, indexed like cls: every kept pixel is initialised (its own launch-relative index
-                            // frame*out_frame_stride + pixel, or SUPER when strong)
-    uint32_t* kept_list;    // launch-relative indices of all kept pixels, in no particular order
+    int32_t* parent;        // union-find slots, indexed like cls: every WEAK pixel is initialised to its own launch-relative index
+                            // frame*out_frame_stride + pixel (strong pixels need no slot: they are final)
+    uint32_t* kept_list;    // launch-relative indices of all weak pixels, in no particular order
     unsigned int* kept_count;  // number of entries (zeroed by the host before the launch)
 };
 
@@ -89,8 +89,9 @@ struct HystParams {
     int row0;              // global row of plane row 0 (the missing-link quirk lives at global (1,0)->(0,1))
     int n_frames;
     int tiles_x, tiles_y;
-    const uint32_t* list;        // kept-pixel list written by front2 (null -> tile-based labelling over the whole plane);
+    const uint32_t* list;        // weak-pixel list written by front2 (null -> tile-based labelling over the whole plane);
     const unsigned int* count;   // the list-driven kernels keep LAUNCH-relative indices (frame*frame_stride + pixel) in parent[]
+    unsigned int* done;          // blocks of the link kernel that have finished (zeroed with the count)
 };
 
 struct UnpackPool;  // api.cu
@@ -140,9 +141,9 @@ struct b200_ctx {
     int band_rows = 0, band_width = 0, band_row0 = 0;
     uint8_t* band_cls = nullptr;          // class map of the resident band (caller's d_edges)
     bool band_sparse = false;             // the resident band's labels were built from the kept-pixel list
-    // kept-pixel count of the last launch of each pipeline slot, copied back asynchronously (pinned host memory, never waited
-    // for): when the previous launch kept more than 1/8 of its pixels the next one uses the tile-based labelling, whose shared-
-    // memory unions win on dense maps.  Both give identical results; a stale value only costs speed.
+    // weak-pixel count of the last launch of each pipeline slot, copied back asynchronously (pinned host memory, never waited
+    // for): when more than 1/8 of the previous launch's pixels were weak the next one uses the tile-based labelling, whose shared-
+    // memory unions win on such maps.  Both give identical results; a stale value only costs speed.
     unsigned int* h_kept = nullptr;       // [4]: slots 0..2 + the band
     long long kept_px[4] = {0, 0, 0, 0};
 };

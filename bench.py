@@ -268,7 +268,9 @@ def run_b200(a, rank, world, local_rank):
     prof = ROOT / "profiles" / "traffic.json"
     if prof.exists():
         try:
-            roofline["traffic"] = json.loads(prof.read_text()).get("front_kernel_dram_bytes_per_launch")
+            # measured on a 4-frame launch (ncu --set full); scaled to this run's launch size
+            per_px = json.loads(prof.read_text()).get("front_kernel_dram_bytes_per_px")
+            roofline["traffic"] = int(per_px * px / front_launches) if per_px else None
         except Exception:
             pass
 

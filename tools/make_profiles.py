@@ -40,6 +40,7 @@ for r in rows[2:]:
 (P / f"{tag}_ncu_full.txt").write_text("\n".join(lines) + "\n")
 (P / "traffic.json").write_text(json.dumps({
     "front_kernel_dram_bytes_per_launch": traffic,
+    "front_kernel_dram_bytes_per_px": round(traffic / 33177600.0, 4),
     "source": f"profiles/{tag}_ncu_full.txt (front2_kernel: dram__bytes_read.sum + dram__bytes_write.sum, one launch = 4 frames 3840x2160 = "
               "33.18 Mpix; part of a launch's 33 MB class map is still in the 126 MB L2 when the launch ends)",
     "algorithmic_bytes_per_launch": 66355200}, indent=1) + "\n")

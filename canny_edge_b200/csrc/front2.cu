@@ -62,7 +62,7 @@ __host__ __device__ constexpr SmemLayout smem_layout(int radius, int slab) {
     o = (o + 127) & ~127;
     L.temp_off = o; o += temp_rows_for(radius, slab) * kTempPitch * 4;
     L.vu_off = o;   o += (slab + 2) * kVuPitch * 4;
-    L.ent_off = o;  o += slab * 32 * 2;                        // candidate lists: at most one 16-bit entry per (class row, lane)
+    L.ent_off = o;  o += slab * 64 * 2;                        // candidate lists: at most one 16-bit entry per (class row, lane, pixel pair)
     L.bits_off = o; o += slab * 4 * 4;                         // kept-pixel bitmap of the slab's class rows: 4 words per row
     L.tab_off = o;  o += 2 * (radius + 1) * (radius + 1) * 4;  // count table, reciprocal table
     L.w_off = o;    o += (2 * radius + 1) * 4;
@@ -100,7 +100,7 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
     constexpr int kRunV = SLAB / 2;            // VU rows per thread in the column pass: 128 columns x 2 halves = 256 threads
     constexpr int kRunCol = kRunV + 2;         // ... which need two more blurred rows
     constexpr int kVuRows = SLAB + 2;
-    constexpr int kEntPerWarp = (SLAB / 8) * 32;
+    constexpr int kEntPerWarp = (SLAB / 8) * 64;
     static_assert(SLAB == 32 || SLAB == 64, "row/column pass mappings are written for 32- and 64-row slabs");
     static_assert(2 * R + 2 <= SLAB, "the saved tail must not overlap the rows it is copied from");
     constexpr SmemLayout L = smem_layout(R, SLAB);
@@ -415,26 +415,30 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
                 const int32_t* vrow = s_vu + q * kVuPitch + 4 * lane;
                 int32_t* nrow = s_np + q * kNpPitch + 4 * lane;
                 uint8_t* o = p.cls + (long long)frame * p.out_frame_stride + (long long)(y_base + q - 1 - p.out_row0) * W + (x0 + 4 * lane);
-                int ent = ((q - 1) << 5) | lane;
+                int ent = ((q - 1) << 6) | (lane << 1);
                 const long long o_step = 8LL * W;
                 // two copies of the loop so the store form is decided once, not per row: the aligned 32-bit store (every strip of
                 // an image whose width is a multiple of 4, except a ragged last strip) or byte stores
                 auto class_row = [&](const int32_t* vr, int32_t* nr, int e16) {
                     const int4 nq = n_of_row(vr);
                     *reinterpret_cast<int4*>(nr) = nq;
-                    const bool any = max(max(nq.x, nq.y), max(nq.z, nq.w)) >= p.lo2;
-                    const unsigned vote = __ballot_sync(0xffffffffu, any);
-                    if (any) my_ent[my_count + __popc(vote & lt_mask)] = (uint16_t)e16;
-                    my_count += __popc(vote);
+                    // one entry per PAIR of pixels (columns 4*lane+1.. +2 and 4*lane+3.. +4) that holds a candidate: candidates
+                    // come in bands a few pixels wide, so pairs leave fewer idle pixel slots in phase 3b than whole quads
+                    const bool any_lo = max(nq.x, nq.y) >= p.lo2, any_hi = max(nq.z, nq.w) >= p.lo2;
+                    const unsigned vote_lo = __ballot_sync(0xffffffffu, any_lo), vote_hi = __ballot_sync(0xffffffffu, any_hi);
+                    const int n_lo = __popc(vote_lo);
+                    if (any_lo) my_ent[my_count + __popc(vote_lo & lt_mask)] = (uint16_t)e16;
+                    if (any_hi) my_ent[my_count + n_lo + __popc(vote_hi & lt_mask)] = (uint16_t)(e16 | 1);
+                    my_count += n_lo + __popc(vote_hi);
                 };
                 // every class word starts out as "suppressed"; phase 3b overwrites the bytes of surviving pixels
                 if (__all_sync(0xffffffffu, word_ok || lane >= kTW / 4)) {
-                    for (; q <= cq_hi; q += 8, vrow += 8 * kVuPitch, nrow += 8 * kNpPitch, o += o_step, ent += 8 << 5) {
+                    for (; q <= cq_hi; q += 8, vrow += 8 * kVuPitch, nrow += 8 * kNpPitch, o += o_step, ent += 8 << 6) {
                         class_row(vrow, nrow, ent);
                         if (lane < kTW / 4) *reinterpret_cast<uint32_t*>(o) = zero_word;
                     }
                 } else {
-                    for (; q <= cq_hi; q += 8, vrow += 8 * kVuPitch, nrow += 8 * kNpPitch, o += o_step, ent += 8 << 5) {
+                    for (; q <= cq_hi; q += 8, vrow += 8 * kVuPitch, nrow += 8 * kNpPitch, o += o_step, ent += 8 << 6) {
                         class_row(vrow, nrow, ent);
                         if (word_ok) {
                             *reinterpret_cast<uint32_t*>(o) = zero_word;
@@ -455,20 +459,20 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
             const int idx_base = (int)out_off;                                // launch-relative pixel index of (class row 0, column j = 1)
             for (int i = lane; i < my_count; i += 32) {
                 const int ent = my_ent[i];
-                const int rr = ent >> 5, el = ent & 31;
-                const int32_t* vrow = s_vu + (rr + 1) * kVuPitch + 4 * el;
-                const int4 qa = *reinterpret_cast<const int4*>(vrow);
-                const int2 qb = *reinterpret_cast<const int2*>(vrow + 4);
-                const int wd[6] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y};
-                const int32_t* nrow = s_np + (rr + 1) * kNpPitch + 4 * el;
-                const int4 n4 = *reinterpret_cast<const int4*>(nrow);
-                const int nc[4] = {n4.x, n4.y, n4.z, n4.w};
-                uint8_t* orow = out_base + (long long)rr * W + 4 * el;
-                // branch-free up to the local-maximum test so the four pixels' chains overlap
-                int na[4], nb[4];
-                bool pass[4];
+                const int rr = ent >> 6, c0 = 2 * (ent & 63);              // pixels j = c0 + 1 and c0 + 2 of class row rr
+                const int32_t* vrow = s_vu + (rr + 1) * kVuPitch + c0;     // VU words j-1 .. j+2 = c0 .. c0+3
+                const int2 qa = *reinterpret_cast<const int2*>(vrow);
+                const int2 qb = *reinterpret_cast<const int2*>(vrow + 2);
+                const int wd[4] = {qa.x, qa.y, qb.x, qb.y};
+                const int32_t* nrow = s_np + (rr + 1) * kNpPitch + c0;     // n[j] lives at word j - 1
+                const int2 n2 = *reinterpret_cast<const int2*>(nrow);
+                const int nc[2] = {n2.x, n2.y};
+                uint8_t* orow = out_base + (long long)rr * W + c0;
+                // branch-free up to the local-maximum test so the two pixels' chains overlap
+                int na[2], nb[2];
+                bool pass[2];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
+                for (int e = 0; e < 2; ++e) {
                     const int n = nc[e];
                     const int wl = wd[e], wc = wd[e + 1], wr = wd[e + 2];
                     const int gx = (int)(short)(wr - wl), gy = (wl + wr + 2 * wc) >> 16;
@@ -488,11 +492,11 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
                     const int off = is0 ? 1 : (is90 ? kNpPitch : (same ? (1 - kNpPitch) : (1 + kNpPitch)));
                     na[e] = nrow[e + off];
                     nb[e] = nrow[e - off];
-                    const int j = 4 * el + 1 + e;
+                    const int j = c0 + 1 + e;
                     pass[e] = (n >= p.lo2) && (j >= 2) && (j <= kTC - 3) && (na[e] < n) && (nb[e] < n);   // j = 1, j >= 126: neighbour-only columns
                 }
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
+                for (int e = 0; e < 2; ++e) {
                     if (pass[e]) {
                         // the reference compares truncated magnitudes: keep iff floor(sqrt(n_nb)) < floor(sqrt(n)) <=> n_nb < mag^2
                         const int n = nc[e];
@@ -506,9 +510,9 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
                                 // pixel is final; its neighbours find it through the class map).  The weak pixel gets its union-
                                 // find slot (itself) and a bit in the slab's bitmap, from which the list entries are made once
                                 // the slab is finished
-                                const int rel = rr * W + 4 * el + e;
+                                const int rel = rr * W + c0 + e;
                                 par_base[rel] = idx_base + rel;
-                                const int col = 4 * el + e - 1;               // class column within the strip: j - 2
+                                const int col = c0 + e - 1;                   // class column within the strip: j - 2
                                 atomicOr(&s_bits[rr * 4 + (col >> 5)], 1u << (col & 31));
                             }
                         }

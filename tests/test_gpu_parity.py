@@ -350,3 +350,34 @@ def test_batch_host_bit_packed_transfer(oracle):
     finally:
         ctx.set_chunk_frames(0)
         ctx.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_fuzz_fused_vs_oracle(gpu_ctx, oracle, seed):
+    """Random sizes (incl. strip / slab boundaries +-1), every compiled radius plus run-time radii, random thresholds and four
+    kinds of content through the fused path (lean kernel + list-driven hysteresis) and the batch API, against the oracle."""
+    rng = np.random.default_rng(1000 + seed)
+    edge_sizes = [2, 3, 63, 64, 65, 123, 124, 125, 127, 128, 129, 247, 248, 249, 255, 256, 257]
+    for case in range(40):
+        h = int(rng.choice(edge_sizes)) if rng.random() < 0.4 else int(rng.integers(2, 420))
+        w = int(rng.choice(edge_sizes)) if rng.random() < 0.4 else int(rng.integers(2, 700))
+        sigma = float(rng.choice([0.5, 0.8, 1.0, 1.4, 1.4, 1.4, 2.0, 3.0, 5.0, 0.6, 2.2]))
+        lo = int(rng.integers(1, 120))
+        hi = int(rng.integers(lo + 1, 256))
+        kind = int(rng.integers(0, 4))
+        if kind == 0:
+            img = rng.integers(0, 256, (h, w)).astype(np.uint8)
+        elif kind == 1:
+            img = cb.synth_host(1, h, w, kind=0, seed=int(rng.integers(1 << 30)))[0]
+        elif kind == 2:   # smooth ramps: long quotient runs near integers, weak gradients around the thresholds
+            yy, xx = np.mgrid[0:h, 0:w]
+            img = ((yy * int(rng.integers(1, 5)) + xx * int(rng.integers(1, 5))) // int(rng.integers(1, 6)) % 256).astype(np.uint8)
+        else:             # blocky content: flat areas with sharp steps
+            img = np.repeat(np.repeat(rng.integers(0, 256, (h // 8 + 1, w // 8 + 1)), 8, 0), 8, 1)[:h, :w].astype(np.uint8)
+        want = oracle.canny(img, sigma, lo, hi)
+        got = cb.cuda_canny(img, sigma, lo, hi, ctx=gpu_ctx)
+        assert_same(f"case {case}: {h}x{w} sigma={sigma} {lo}/{hi} kind={kind}", got, want)
+        if case % 8 == 0:
+            out = cb.canny_batch_host(np.stack([img, img[::-1].copy()]), sigma, lo, hi, ctx=gpu_ctx)
+            assert_same("batch[0]", out[0].astype(np.int16), want)
+            assert_same("batch[1]", out[1].astype(np.int16), oracle.canny(img[::-1].copy(), sigma, lo, hi))

@@ -55,10 +55,14 @@ __host__ __device__ constexpr int temp_rows_for(int radius, int slab) {
 struct SmemLayout {
     int in_off, temp_off, vu_off, ent_off, bits_off, tab_off, w_off, bar_off, total;
 };
+// staged input slabs: two (the next slab's TMA is in flight while this one is blurred) unless the wide temp buffer of a large
+// radius would then push a CTA past half an SM's shared memory — with one buffer the next slab is requested as soon as the row
+// pass has read this one and lands during the column pass and phase 3
+__host__ __device__ constexpr int in_bufs_for(int radius) { return radius > 9 ? 1 : 2; }
 __host__ __device__ constexpr SmemLayout smem_layout(int radius, int slab) {
     SmemLayout L{};
     int o = 0;
-    L.in_off = o;   o += 2 * slab * in_pitch_for(radius);
+    L.in_off = o;   o += in_bufs_for(radius) * slab * in_pitch_for(radius);
     o = (o + 127) & ~127;
     L.temp_off = o; o += temp_rows_for(radius, slab) * kTempPitch * 4;
     L.vu_off = o;   o += (slab + 2) * kVuPitch * 4;
@@ -161,12 +165,13 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
     const uint8_t* in_frame = p.in + (long long)frame * p.in_frame_stride;
     constexpr uint32_t slab_bytes = (uint32_t)(kSlab * in_pitch);
 
+    constexpr int kInBufs = in_bufs_for(R);
     auto issue_slab = [&](int k) {
         const int gy = in_y0 + k * kSlab;
-        unsigned char* dst = s_in + (k & 1) * slab_bytes;
+        unsigned char* dst = s_in + (k % kInBufs) * slab_bytes;
         if (USE_TMA) {
             if (tid == 0) {
-                const uint32_t bar = bar0 + 8 * (k & 1);
+                const uint32_t bar = bar0 + 8 * (k % kInBufs);
                 mbar_expect_tx(bar, slab_bytes);
                 tma_load_3d(smem_u32(dst), &tmap, bar, in_x0, gy - p.in_row0, frame);
             }
@@ -185,7 +190,7 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
 
     if (USE_TMA) {
         issue_slab(0);
-        if (n_slabs > 1) issue_slab(1);
+        if (kInBufs > 1 && n_slabs > 1) issue_slab(1);
     }
 
     // kept-pixel list entries of the previous slab, waiting for their reservation (see the end of the loop body)
@@ -207,12 +212,12 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
     for (int k = 0; k < n_slabs; ++k) {
         const int I_k = in_y0 + k * kSlab;  // global row of this slab's first input line
         if (USE_TMA) {
-            mbar_wait(bar0 + 8 * (k & 1), (uint32_t)((k >> 1) & 1));
+            mbar_wait(bar0 + 8 * (k % kInBufs), (uint32_t)((k / kInBufs) & 1));
         } else {
             issue_slab(k);
             __syncthreads();
         }
-        const unsigned char* slab = s_in + (k & 1) * slab_bytes;
+        const unsigned char* slab = s_in + (k % kInBufs) * slab_bytes;
 
         // ===================== phase 1: row blur, u8 -> f32 (src/utils.cpp:37-49) =====================
         // thread = (slab row 32*(warp>>2) + lane, 32 columns starting at 32*(warp&3)); temp buffer row T0 + slab row
@@ -286,7 +291,7 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
         }
         if (sparse) flush_pending();
         __syncthreads();  // (A) this slab's temp lines are complete; staged buffer k&1 is free again
-        if (USE_TMA && k + 2 < n_slabs) issue_slab(k + 2);
+        if (USE_TMA && k + kInBufs < n_slabs) issue_slab(k + kInBufs);
 
         // ===================== phase 2: column blur f32 -> int (src/utils.cpp:52-64) + vertical half of Sobel =====================
         // thread = (column tid&127, half tid>>7).  Blurred rows Bg(o) = I_k - R - 2 + 32*half + o, o = 0..33, from temp buffer

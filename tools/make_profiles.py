@@ -53,7 +53,7 @@ for r in rows[1:]:
     agg[r[ik].split("(")[0]].append(float(r[iv].replace(",", "")))
 pipe = {k: v for k, v in agg.items() if not any(s in k for s in ("synth", "count255", "div1_check", "div3_check"))}
 tot = sum(sum(v) for v in pipe.values())
-out = ["# per-kernel device time of `bench.py --frames 16 --steps 2 --warmup 3 --no-e2e --no-cpu` under ncu (cold-cache, serialised: shares, not absolutes)"]
+out = ["# per-kernel device time of `bench.py --frames 18 --steps 2 --warmup 3 --no-e2e --no-cpu` under ncu (cold-cache, serialised: shares, not absolutes)"]
 for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
     share = f"{sum(v) / tot:.3f}" if k in pipe else "  -  "
     out.append(f"{k[:64]:64s} launches={len(v):3d} total_us={sum(v) / 1e3:9.1f} share_of_pipeline={share} avg_us={sum(v) / len(v) / 1e3:8.1f}")

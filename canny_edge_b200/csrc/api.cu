@@ -245,7 +245,7 @@ static int run_frames_device(b200_ctx* ctx, cudaStream_t st, int slot, const uin
     fp.blur = blur; fp.mag = mag; fp.ang = ang; fp.nms = nms;
     fp.w = ctx->gauss.d_w; fp.count = ctx->gauss.d_count; fp.radius = ctx->gauss.radius;
     fill_thresholds(fp, lo, hi);
-    // sparse hand-over to hysteresis (used when the lean front kernel runs): union-find slots + kept-pixel bitmap
+    // sparse hand-over to hysteresis (used when the lean front kernel runs): union-find slots + weak-pixel list
     fp.parent = reinterpret_cast<int32_t*>(ctx->ws_parent[slot].ptr);
     fp.kept_count = reinterpret_cast<unsigned int*>(ctx->ws_list[slot].ptr);
     fp.kept_list = reinterpret_cast<uint32_t*>(ctx->ws_list[slot].ptr) + 16;
@@ -269,7 +269,7 @@ static int run_frames_device(b200_ctx* ctx, cudaStream_t st, int slot, const uin
     return B200_OK;
 }
 
-// bytes of the kept-pixel list for nf frames of h x w: a counter block + one 32-bit entry per pixel (worst case: all kept)
+// bytes of the weak-pixel list for nf frames of h x w: a counter block + one 32-bit entry per pixel (worst case: all weak)
 static size_t list_bytes(int nf, int h, int w) { return 64 + (size_t)nf * (size_t)h * (size_t)w * 4; }
 
 static int auto_chunk_frames(const b200_ctx* ctx, int h, int w, int n_frames) {

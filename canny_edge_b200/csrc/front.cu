@@ -1,6 +1,9 @@
-// front.cu — fused stages 1-3 of the Canny hot path for sm_100a:
+// front.cu — fused stages 1-3 of the Canny hot path for sm_100a, GENERAL variant:
 //   u8 gray  --row blur-->  f32  --column blur + truncate-->  i16 blur  --Sobel-->  (gx,gy)
 //            --magnitude / direction / non-max suppression / double threshold-->  u8 class map
+// It serves what the lean kernel of front2.cu does not: run-time radii (sigma outside the compiled set), the int16 spill planes
+// of the stage API / `steps` (blur, magnitude, angle, nms), and sigma so small that sums approach the subnormal range.  The
+// dispatcher launch_front() at the end of this file picks between the two; both are parity-tested against the oracle.
 //
 // Replaces the reference's three kernels gaussian_util / sobel_util / nonmaximal_utility
 // (src/cuda.cu:32-73,104-218,249-363) and the host round trips between them

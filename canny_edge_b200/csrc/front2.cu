@@ -67,7 +67,7 @@ __host__ __device__ constexpr SmemLayout smem_layout(int radius, int slab) {
     L.temp_off = o; o += temp_rows_for(radius, slab) * kTempPitch * 4;
     L.vu_off = o;   o += (slab + 2) * kVuPitch * 4;
     L.ent_off = o;  o += slab * 64 * 2;                        // candidate lists: at most one 16-bit entry per (class row, lane, pixel pair)
-    L.bits_off = o; o += slab * 4 * 4;                         // kept-pixel bitmap of the slab's class rows: 4 words per row
+    L.bits_off = o; o += slab * 4 * 4;                         // weak-pixel bitmap of the slab's class rows: 4 words per row
     L.tab_off = o;  o += 2 * (radius + 1) * (radius + 1) * 4;  // count table, reciprocal table
     L.w_off = o;    o += (2 * radius + 1) * 4;
     o = (o + 15) & ~15;
@@ -193,7 +193,7 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
         if (kInBufs > 1 && n_slabs > 1) issue_slab(1);
     }
 
-    // kept-pixel list entries of the previous slab, waiting for their reservation (see the end of the loop body)
+    // weak-pixel list entries of the previous slab, waiting for their reservation (see the end of the loop body)
     uint32_t pend_bits = 0;
     unsigned int pend_base = 0;
     int pend_off = 0, pend_g0 = 0;
@@ -525,7 +525,7 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
                 }
             }
         }
-        __syncthreads();  // (C) VU, n-plane and list reads done; the slab's kept-pixel bitmap is complete
+        __syncthreads();  // (C) VU, n-plane and list reads done; the slab's weak-pixel bitmap is complete
         if (sparse) {
             // append this slab's weak pixels to the launch-wide list: every warp counts the bits of its 32 bitmap words and reserves
             // room with ONE global atomicAdd.  The atomic's round trip is hidden behind the next slab's row pass: the entries are

@@ -17,6 +17,7 @@ import numpy as np
 HERE = Path(__file__).resolve().parent
 ORACLE_LIB = HERE / "liboracle.so"
 REF_LIB = HERE / "_ref" / "libcanny_ref.so"
+REF_LIB_O0 = HERE / "_ref" / "libcanny_ref_O0.so"   # same sources at -O0 (what the reference's CMake builds); timing only
 
 
 def build(verbose: bool = False) -> None:
@@ -130,8 +131,8 @@ class Oracle(_Base):
 class Ref(_Base):
     prefix = "ref_"
 
-    def __init__(self):
-        super().__init__(REF_LIB)
+    def __init__(self, path: Path = REF_LIB):
+        super().__init__(path)
         self.lib.ref_canny.restype = C.c_double
 
     @staticmethod

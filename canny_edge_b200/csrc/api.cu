@@ -252,7 +252,8 @@ static int run_frames_device(b200_ctx* ctx, cudaStream_t st, int slot, const uin
     CB_CUDA(cudaMemsetAsync(fp.kept_count, 0, 2 * sizeof(unsigned int), st));   // list length + link-kernel block counter
     bool sparse = false;
     CB_TRY(launch_front(ctx, st, fp, &sparse));
-    const bool dense = ctx->kept_px[slot] > 0 && (long long)ctx->h_kept[slot] * 8 > ctx->kept_px[slot];   // previous launch of this slot
+    static const long long dense_div = [] { const char* e = getenv("B200_CANNY_DENSE_DIV"); return e ? atoll(e) : 8LL; }();
+    const bool dense = ctx->kept_px[slot] > 0 && (long long)ctx->h_kept[slot] * dense_div > ctx->kept_px[slot];   // previous launch of this slot
     if (sparse) {
         CB_CUDA(cudaMemcpyAsync(&ctx->h_kept[slot], fp.kept_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
         ctx->kept_px[slot] = (long long)nf * px;

@@ -36,7 +36,13 @@ ctx.set_chunk_frames(a.chunk)
 n, h, w = a.frames, a.height, a.width
 d_in = torch.empty((n, h, w), dtype=torch.uint8, device="cuda")
 d_out = torch.empty_like(d_in)
-check(lib.b200_synth_device(ctx.handle, d_in.data_ptr(), n, h, w, a.kind, 1234, 0))
+if a.kind >= 0:
+    check(lib.b200_synth_device(ctx.handle, d_in.data_ptr(), n, h, w, a.kind, 1234, 0))
+else:
+    # --kind -1: the reference's tests/test.jpg (decoded gray, committed as raw bytes) tiled over every frame
+    import numpy as np
+    tile = torch.from_numpy(np.fromfile(Path(__file__).resolve().parents[1] / "tests" / "golden" / "test_gray_256x256.u8", dtype=np.uint8).reshape(256, 256)).cuda()
+    d_in[:] = tile.repeat(-(-h // 256), -(-w // 256))[:h, :w]
 torch.cuda.synchronize()
 px = n * h * w
 

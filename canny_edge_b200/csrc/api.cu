@@ -5,7 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
-#include <emmintrin.h>  // _mm_stream_si64 / _mm_sfence (SSE2, x86-64 baseline): non-temporal stores of the expanded edge map
+#include <emmintrin.h>  // _mm_stream_si64 / _mm_stream_si128 / _mm_sfence (SSE2, x86-64 baseline): non-temporal stores of the expanded edge map
 
 #include <algorithm>
 #include <condition_variable>
@@ -117,51 +117,81 @@ int prepare_gauss(b200_ctx* ctx, float sigma) {
     return B200_OK;
 }
 
-// ---- host side of the bit-packed edge transfer ---------------------------------------------------------------
+// ---- host side of the transfers: a small thread pool -------------------------------------------------------------
 // b200_canny_batch_host sends the edge map over PCIe as 1 bit per pixel (the link is the bottleneck of the host path: with both
-// directions carrying 1 B/px it saturates at ~46 GB/s each way) and expands it to the 0 / 255 bytes of the reference's result
-// on the host, with a small pool of threads that runs while the GPU works on the following chunks.
-struct UnpackPool {
+// directions carrying 1 B/px it saturates at ~46 GB/s each way) and expands it to the 0 / 255 bytes (or int16 values) of the
+// reference's result on the host, with a small pool of threads that runs while the GPU works on the following chunks.  The same
+// pool copies PAGEABLE caller buffers into the context's pinned staging memory: a cudaMemcpy from pageable memory goes through
+// the driver's own single-threaded staging (~10 GB/s); several threads filling a pinned buffer that is then DMA'd are 2-3x faster.
+struct HostPool {
+    enum Job { kUnpackU8, kUnpackI16, kCopy };
     std::vector<std::thread> workers;
     std::mutex mu;
     std::condition_variable cv_go, cv_done;
+    Job job = kCopy;
     const uint8_t* src = nullptr;
     uint8_t* dst = nullptr;
-    size_t n_px = 0;
+    size_t n_items = 0;   // pixels (unpack jobs) or bytes (copy)
     int generation = 0, pending = 0;
     bool stop = false;
-    uint64_t lut[256];
+    uint64_t lut[256];                    // bit pattern -> eight 0 / 255 bytes
+    alignas(16) int16_t lut16[256][8];    // bit pattern -> eight 0 / 255 int16 values
 
-    explicit UnpackPool(int n_threads) {
+    explicit HostPool(int n_threads) {
         for (int b = 0; b < 256; ++b) {
             uint64_t v = 0;
-            for (int i = 0; i < 8; ++i) if (b & (1 << i)) v |= 0xFFull << (8 * i);
+            for (int i = 0; i < 8; ++i) {
+                if (b & (1 << i)) v |= 0xFFull << (8 * i);
+                lut16[b][i] = (b & (1 << i)) ? 255 : 0;
+            }
             lut[b] = v;
         }
         for (int t = 0; t < n_threads; ++t) workers.emplace_back([this, t] { loop(t); });
     }
-    ~UnpackPool() {
+    ~HostPool() {
         { std::lock_guard<std::mutex> lk(mu); stop = true; }
         cv_go.notify_all();
         for (auto& w : workers) w.join();
     }
     int parts() const { return (int)workers.size() + 1; }
-    void slice(int part) {  // part-th of parts() slices, on 64-byte-of-output boundaries
-        const size_t n_bytes_in = n_px / 8;
-        const size_t per = ((n_bytes_in + parts() - 1) / parts() + 7) & ~(size_t)7;
-        const size_t b0 = std::min(n_bytes_in, per * (size_t)part), b1 = std::min(n_bytes_in, b0 + per);
-        if ((reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
-            // streaming stores: the 64 bytes made from 8 input bytes fill one cache line, so the line is written without first
-            // being read (the host path is bound by host-memory traffic: PCIe reads the frames from the same DRAM)
-            long long* out = reinterpret_cast<long long*>(dst);
-            for (size_t i = b0; i < b1; ++i) _mm_stream_si64(out + i, (long long)lut[src[i]]);
-            _mm_sfence();
+    // units [u0, u1) of the current job: a unit is one packed input byte (8 pixels) for the unpack jobs, 64 bytes for a copy
+    void range(size_t u0, size_t u1) {
+        if (job == kCopy) {
+            const size_t b0 = std::min(n_items, u0 * 64), b1 = std::min(n_items, u1 * 64);
+            memcpy(dst + b0, src + b0, b1 - b0);
+        } else if (job == kUnpackU8) {
+            if ((reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+                // streaming stores: the 64 bytes made from 8 input bytes fill one cache line, so the line is written without
+                // first being read (the host path is bound by host-memory traffic: PCIe reads the frames from the same DRAM)
+                long long* out = reinterpret_cast<long long*>(dst);
+                for (size_t i = u0; i < u1; ++i) _mm_stream_si64(out + i, (long long)lut[src[i]]);
+                _mm_sfence();
+            } else {
+                for (size_t i = u0; i < u1; ++i) memcpy(dst + 8 * i, &lut[src[i]], 8);
+            }
         } else {
-            for (size_t i = b0; i < b1; ++i) memcpy(dst + 8 * i, &lut[src[i]], 8);
+            if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                __m128i* out = reinterpret_cast<__m128i*>(dst);
+                for (size_t i = u0; i < u1; ++i) _mm_stream_si128(out + i, _mm_load_si128(reinterpret_cast<const __m128i*>(lut16[src[i]])));
+                _mm_sfence();
+            } else {
+                for (size_t i = u0; i < u1; ++i) memcpy(dst + 16 * i, lut16[src[i]], 16);
+            }
         }
-        if (part == parts() - 1) {  // the last few pixels when n_px is not a multiple of 8
-            for (size_t px = 8 * n_bytes_in; px < n_px; ++px) dst[px] = ((src[px >> 3] >> (px & 7)) & 1) ? 255 : 0;
+    }
+    size_t units() const { return job == kCopy ? (n_items + 63) / 64 : n_items / 8; }
+    void tail() {  // the last few pixels of an unpack job whose pixel count is not a multiple of 8
+        if (job == kCopy) return;
+        for (size_t px = 8 * (n_items / 8); px < n_items; ++px) {
+            const int v = ((src[px >> 3] >> (px & 7)) & 1) ? 255 : 0;
+            if (job == kUnpackU8) dst[px] = (uint8_t)v; else reinterpret_cast<int16_t*>(dst)[px] = (int16_t)v;
         }
+    }
+    void slice(int part) {  // part-th of parts() slices, on multiples of 8 units
+        const size_t n = units();
+        const size_t per = ((n + parts() - 1) / parts() + 7) & ~(size_t)7;
+        const size_t u0 = std::min(n, per * (size_t)part), u1 = std::min(n, u0 + per);
+        range(u0, u1);
     }
     void loop(int t) {
         int seen = 0;
@@ -179,20 +209,60 @@ struct UnpackPool {
             }
         }
     }
-    // expands n_px bits at `s` into n_px bytes at `d`; returns when done (the caller's thread takes a slice too)
-    void run(const uint8_t* s, uint8_t* d, size_t n) {
+    // runs one job over n items and returns when it is done; the caller's thread takes a slice too.  Jobs too small to be worth
+    // waking the workers (a few microseconds of work) run on the caller's thread alone.
+    void run(Job j, const void* s, void* d, size_t n) {
+        const size_t out_bytes = j == kCopy ? n : (j == kUnpackU8 ? n : 2 * n);
+        if (workers.empty() || out_bytes < (256u << 10)) {
+            job = j; src = static_cast<const uint8_t*>(s); dst = static_cast<uint8_t*>(d); n_items = n;
+            range(0, units());
+            tail();
+            return;
+        }
         {
             std::lock_guard<std::mutex> lk(mu);
-            src = s; dst = d; n_px = n;
+            job = j; src = static_cast<const uint8_t*>(s); dst = static_cast<uint8_t*>(d); n_items = n;
             pending = (int)workers.size();
             ++generation;
         }
         cv_go.notify_all();
         slice(parts() - 1);
+        tail();
         std::unique_lock<std::mutex> lk(mu);
         cv_done.wait(lk, [&] { return pending == 0; });
     }
 };
+
+// measured on the B200 hosts (tools/e2e_probe.py, tools/e2e_multi.sh): 4 threads (3 workers + the caller) keep up with the link
+// when one process owns the host (e2e 52.7 Gpix/s with 4, 50 with 6-8, 45 with 10, 34 with 16 threads: more of them only fight
+// the DMA engine for host-memory bandwidth); with 8 processes on a 32-vCPU host 2 each are best (aggregate 131 Gpix/s against 87
+// with 4 and 104 with 1).  LOCAL_WORLD_SIZE is what torchrun exports.
+static HostPool* get_pool(b200_ctx* ctx) {
+    if (!ctx->pool) {
+        unsigned hc = std::thread::hardware_concurrency();
+        int local_world = 1;
+        if (const char* e = getenv("LOCAL_WORLD_SIZE")) local_world = std::max(1, atoi(e));
+        int n_threads = (int)std::min<unsigned>(std::max<unsigned>((hc ? hc : 4) / (2u * (unsigned)local_world), 1), 4) - 1;
+        if (const char* e = getenv("B200_CANNY_UNPACK_THREADS")) n_threads = std::max(0, atoi(e) - 1);
+        ctx->pool = new HostPool(std::max(0, n_threads));
+    }
+    return ctx->pool;
+}
+
+// Staging pageable memory through the pool pays for large jobs only (measured on the B200 hosts, tools/latency_probe.py: an
+// 8192x8192 frame from / to pageable memory 13.6 -> 6.3 ms with int16 output, 8.5 -> 5.8 ms with byte output; a 1080p or 4K frame
+// gets slower, the thread wake-ups and the hosts' modest per-core memory bandwidth cost more than the driver's own pageable path)
+constexpr long long kStageMinBytes = 32LL << 20;
+
+// true when `p` is ordinary pageable host memory (not pinned / registered / managed): such buffers are staged by the pool
+static bool is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
 
 static std::mutex g_default_mu;
 static b200_ctx* g_default_ctx = nullptr;
@@ -315,16 +385,25 @@ int b200_ctx_create(int device, b200_ctx** out) {
     b200_ctx* c = new b200_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    CB_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-    c->stream = c->own_stream;
-    for (int i = 0; i < 3; ++i) {
-        CB_CUDA(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
-        CB_CUDA(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
-        CB_CUDA(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming | cudaEventBlockingSync));
+    auto init = [&]() -> int {
+        CB_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+        c->stream = c->own_stream;
+        for (int i = 0; i < 3; ++i) {
+            CB_CUDA(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
+            CB_CUDA(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+            CB_CUDA(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming | cudaEventBlockingSync));
+            CB_CUDA(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+        }
+        CB_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        CB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_kept), 4 * sizeof(unsigned int)));
+        memset(c->h_kept, 0, 4 * sizeof(unsigned int));
+        return B200_OK;
+    };
+    const int rc = init();
+    if (rc != B200_OK) {   // release whatever was created (the destroy path skips null members)
+        b200_ctx_destroy(c);
+        return rc;
     }
-    CB_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-    CB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_kept), 4 * sizeof(unsigned int)));
-    memset(c->h_kept, 0, 4 * sizeof(unsigned int));
     *out = c;
     return B200_OK;
 }
@@ -342,6 +421,8 @@ int b200_ctx_destroy(b200_ctx* c) {
         if (c->side[i]) cudaStreamDestroy(c->side[i]);
         if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
         if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
+        if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+        rel(c->host_in[i], true);
         rel(c->dev_bits[i], false);
         rel(c->host_bits[i], true);
     }
@@ -527,7 +608,19 @@ int b200_canny_steps(b200_ctx* ctx, const uint8_t* img, float sigma, int lo, int
     return B200_OK;
 }
 
+static int batch_host_impl(b200_ctx* ctx, const uint8_t* frames, int n_frames, int h, int w, int lo, int hi, uint8_t* edges8,
+                           int16_t* edges16, bool packed);
+static bool packed_transfer_off();
+
 int b200_canny(b200_ctx* ctx, const uint8_t* img, float sigma, int lo, int hi, int h, int w, int16_t* edges) {
+    // large frames in pageable memory take the pipelined host path: the frame is staged through pinned memory by the host pool,
+    // the map crosses PCIe bit-packed (1/16 of the int16 plane) and is expanded to the reference's 0 / 255 int16 values by the pool
+    if ((long long)h * w >= kStageMinBytes && !packed_transfer_off() && img && edges && (is_pageable(img) || is_pageable(edges))) {
+        CB_TRY(check_image(img, edges, h, w));
+        CB_TRY(resolve_ctx(ctx));
+        CB_TRY(prepare_gauss(ctx, sigma));
+        return batch_host_impl(ctx, img, 1, h, w, lo, hi, nullptr, edges, true);
+    }
     return b200_canny_steps(ctx, img, sigma, lo, hi, h, w, nullptr, nullptr, nullptr, nullptr, edges);
 }
 
@@ -547,15 +640,44 @@ int b200_canny_bgr(b200_ctx* ctx, const uint8_t* bgr, float sigma, int lo, int h
     CB_TRY(ensure_ws(ctx->ws_parent[0], (size_t)px * 4));
     CB_TRY(ensure_ws(ctx->ws_list[0], list_bytes(1, h, w)));
     cudaStream_t st = ctx->stream;
+    // large frames in pageable memory: staged through pinned memory by the host pool, edge map back bit-packed (see
+    // batch_host_impl); everything else takes the plain copies
+    const bool fast = 3 * px >= kStageMinBytes && !packed_transfer_off() && (is_pageable(bgr) || is_pageable(edges));
+    HostPool* pool = fast ? get_pool(ctx) : nullptr;
     // the 3-byte frame is staged in the int16 scratch planes (p16[0..1] hold 4*px bytes >= 3*px)
     uint8_t* d_bgr = reinterpret_cast<uint8_t*>(pl.p16[0]);
-    CB_CUDA(cudaMemcpyAsync(d_bgr, bgr, (size_t)px * 3, cudaMemcpyHostToDevice, st));
+    const uint8_t* h_src = bgr;
+    if (fast && is_pageable(bgr)) {
+        CB_TRY(ensure_ws(ctx->host_in[0], (size_t)px * 3, /*pinned_host=*/true));
+        if (ctx->in_busy[0]) { CB_CUDA(cudaEventSynchronize(ctx->ev_in[0])); ctx->in_busy[0] = false; }
+        pool->run(HostPool::kCopy, bgr, ctx->host_in[0].ptr, (size_t)px * 3);
+        h_src = reinterpret_cast<const uint8_t*>(ctx->host_in[0].ptr);
+    }
+    CB_CUDA(cudaMemcpyAsync(d_bgr, h_src, (size_t)px * 3, cudaMemcpyHostToDevice, st));
     CB_TRY(launch_bgr_to_gray(ctx, st, d_bgr, pl.in, (size_t)px));
     CB_TRY(run_frames_device(ctx, st, 0, pl.in, pl.cls, 1, h, w, lo, hi, nullptr, nullptr, nullptr, nullptr));
-    CB_TRY(launch_expand_u8_to_i16(ctx, st, pl.cls, pl.p16[4], (size_t)px));
-    if (gray_out) CB_CUDA(cudaMemcpyAsync(gray_out, pl.in, (size_t)px, cudaMemcpyDeviceToHost, st));
-    CB_CUDA(cudaMemcpyAsync(edges, pl.p16[4], (size_t)px * 2, cudaMemcpyDeviceToHost, st));
+    if (!fast) {
+        CB_TRY(launch_expand_u8_to_i16(ctx, st, pl.cls, pl.p16[4], (size_t)px));
+        if (gray_out) CB_CUDA(cudaMemcpyAsync(gray_out, pl.in, (size_t)px, cudaMemcpyDeviceToHost, st));
+        CB_CUDA(cudaMemcpyAsync(edges, pl.p16[4], (size_t)px * 2, cudaMemcpyDeviceToHost, st));
+        CB_CUDA(cudaStreamSynchronize(st));
+        return B200_OK;
+    }
+    const size_t bits_bytes = (((size_t)px + 31) / 32) * 4;
+    CB_TRY(ensure_ws(ctx->dev_bits[0], bits_bytes));
+    CB_TRY(ensure_ws(ctx->host_bits[0], bits_bytes, /*pinned_host=*/true));
+    CB_TRY(launch_pack_edges(ctx, st, pl.cls, reinterpret_cast<uint32_t*>(ctx->dev_bits[0].ptr), (size_t)px));
+    CB_CUDA(cudaMemcpyAsync(ctx->host_bits[0].ptr, ctx->dev_bits[0].ptr, bits_bytes, cudaMemcpyDeviceToHost, st));
+    const bool stage_gray = gray_out && is_pageable(gray_out);
+    if (stage_gray) {
+        CB_TRY(ensure_ws(ctx->host_in[1], (size_t)px, /*pinned_host=*/true));
+        CB_CUDA(cudaMemcpyAsync(ctx->host_in[1].ptr, pl.in, (size_t)px, cudaMemcpyDeviceToHost, st));
+    } else if (gray_out) {
+        CB_CUDA(cudaMemcpyAsync(gray_out, pl.in, (size_t)px, cudaMemcpyDeviceToHost, st));
+    }
     CB_CUDA(cudaStreamSynchronize(st));
+    pool->run(HostPool::kUnpackI16, ctx->host_bits[0].ptr, edges, (size_t)px);
+    if (stage_gray) pool->run(HostPool::kCopy, ctx->host_in[1].ptr, gray_out, (size_t)px);
     return B200_OK;
 }
 
@@ -594,21 +716,19 @@ int b200_canny_batch_device(b200_ctx* ctx, const uint8_t* d_frames, int n_frames
     return B200_OK;
 }
 
-int b200_canny_batch_host(b200_ctx* ctx, const uint8_t* frames, int n_frames, int h, int w, float sigma, int lo, int hi,
-                          uint8_t* edges) {
-    CB_TRY(check_image(frames, edges, h, w));
-    if (n_frames <= 0) { set_error("n_frames must be positive"); return B200_ERR_INVALID_ARG; }
-    CB_TRY(resolve_ctx(ctx));
-    CB_TRY(prepare_gauss(ctx, sigma));
+// Host buffers in, host buffers out: frames -> 0 / 255 edge maps, as bytes (edges8) or as the reference's int16 (edges16).
+// Chunks of frames are pipelined over three stream slots (H2D | kernels | D2H + host expansion).  Pageable caller memory is staged
+// through pinned buffers by the host pool; the maps come back bit-packed unless the job is small AND the output buffer is pinned.
+static int batch_host_impl(b200_ctx* ctx, const uint8_t* frames, int n_frames, int h, int w, int lo, int hi, uint8_t* edges8,
+                           int16_t* edges16, bool packed) {
     const long long px = (long long)h * w;
-    // chunks of ~64 MB: big enough for full PCIe rate, small enough that three are in flight (H2D | kernels | D2H + host unpack)
+    // chunks of ~64 MB: big enough for full PCIe rate, small enough that three are in flight
     int chunk = ctx->chunk_frames > 0 ? ctx->chunk_frames : (int)std::max<long long>(1, (64LL << 20) / px);
     chunk = std::min(chunk, n_frames);
     const int n_chunks = (n_frames + chunk - 1) / chunk;
     const int n_slots = std::min(3, n_chunks);
-    static const bool packed_off = [] { const char* e = getenv("B200_CANNY_NO_PACKED_D2H"); return e && e[0] == '1'; }();
-    // small jobs are latency-bound: the byte map goes back directly (no pack kernel, no host pass)
-    const bool packed = !packed_off && (long long)n_frames * px >= (8LL << 20);
+    const bool stage_in = is_pageable(frames) && (long long)n_frames * px >= kStageMinBytes;
+    if (edges16 && !packed) { set_error("internal: int16 output needs the packed path"); return B200_ERR_INVALID_ARG; }
     const size_t chunk_bits_bytes = (((size_t)px * (size_t)chunk + 31) / 32) * 4;
     for (int s = 0; s < n_slots; ++s) {
         CB_TRY(ensure_ws(ctx->ws_parent[s], (size_t)px * 4 * (size_t)chunk));
@@ -619,26 +739,18 @@ int b200_canny_batch_host(b200_ctx* ctx, const uint8_t* frames, int n_frames, in
             CB_TRY(ensure_ws(ctx->dev_bits[s], chunk_bits_bytes));
             CB_TRY(ensure_ws(ctx->host_bits[s], chunk_bits_bytes, /*pinned_host=*/true));
         }
+        if (stage_in) CB_TRY(ensure_ws(ctx->host_in[s], (size_t)px * (size_t)chunk, /*pinned_host=*/true));
     }
-    if (packed && !ctx->pool) {
-        // measured on the B200 hosts (tools/e2e_probe.py, tools/e2e_multi.sh): 4 expanding threads (3 workers + the caller) keep up
-        // with the link when one process owns the host (e2e 52.7 Gpix/s with 4, 50 with 6-8, 45 with 10, 34 with 16 threads: more
-        // of them only fight the DMA engine for host-memory bandwidth); with 8 processes on a 32-vCPU host 2 each are best
-        // (aggregate 131 Gpix/s against 87 with 4 and 104 with 1).  LOCAL_WORLD_SIZE is what torchrun exports.
-        unsigned hc = std::thread::hardware_concurrency();
-        int local_world = 1;
-        if (const char* e = getenv("LOCAL_WORLD_SIZE")) local_world = std::max(1, atoi(e));
-        int n_threads = (int)std::min<unsigned>(std::max<unsigned>((hc ? hc : 4) / (2u * (unsigned)local_world), 1), 4) - 1;
-        if (const char* e = getenv("B200_CANNY_UNPACK_THREADS")) n_threads = std::max(0, atoi(e) - 1);
-        ctx->pool = new UnpackPool(std::max(0, n_threads));
-    }
+    HostPool* pool = (packed || stage_in) ? get_pool(ctx) : nullptr;
     CB_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
     for (int s = 0; s < n_slots; ++s) CB_CUDA(cudaStreamWaitEvent(ctx->side[s], ctx->ev_fork, 0));
     auto finish_chunk = [&](int c) -> int {  // host side of chunk c: wait for its packed map, expand it into the caller's buffer
         const int f0 = c * chunk, nf = std::min(chunk, n_frames - f0);
         const int s = c % n_slots;
         CB_CUDA(cudaEventSynchronize(ctx->ev_chunk[s]));
-        ctx->pool->run(reinterpret_cast<const uint8_t*>(ctx->host_bits[s].ptr), edges + (long long)f0 * px, (size_t)px * nf);
+        const uint8_t* bits = reinterpret_cast<const uint8_t*>(ctx->host_bits[s].ptr);
+        if (edges16) pool->run(HostPool::kUnpackI16, bits, edges16 + (long long)f0 * px, (size_t)px * nf);
+        else pool->run(HostPool::kUnpackU8, bits, edges8 + (long long)f0 * px, (size_t)px * nf);
         return B200_OK;
     };
     for (int c = 0; c < n_chunks; ++c) {
@@ -648,8 +760,15 @@ int b200_canny_batch_host(b200_ctx* ctx, const uint8_t* frames, int n_frames, in
         uint8_t* din = reinterpret_cast<uint8_t*>(ctx->dev_in[s].ptr);
         uint8_t* dout = reinterpret_cast<uint8_t*>(ctx->dev_out[s].ptr);
         // slot reuse: chunk c's device buffers are ordered by the stream; its pinned host_bits[s] was consumed by
-        // finish_chunk(c - n_slots), which ran before this iteration (see below)
-        CB_CUDA(cudaMemcpyAsync(din, frames + (long long)f0 * px, (size_t)px * nf, cudaMemcpyHostToDevice, st));
+        // finish_chunk(c - n_slots), which ran before this iteration (see below); host_in[s] is free once ev_in[s] has fired
+        const uint8_t* h_src = frames + (long long)f0 * px;
+        if (stage_in) {
+            if (ctx->in_busy[s]) { CB_CUDA(cudaEventSynchronize(ctx->ev_in[s])); ctx->in_busy[s] = false; }
+            pool->run(HostPool::kCopy, h_src, ctx->host_in[s].ptr, (size_t)px * nf);
+            h_src = reinterpret_cast<const uint8_t*>(ctx->host_in[s].ptr);
+        }
+        CB_CUDA(cudaMemcpyAsync(din, h_src, (size_t)px * nf, cudaMemcpyHostToDevice, st));
+        if (stage_in) { CB_CUDA(cudaEventRecord(ctx->ev_in[s], st)); ctx->in_busy[s] = true; }
         ctx->h2d_bytes += (unsigned long long)px * nf;
         ctx->d2h_bytes += packed ? (unsigned long long)(((size_t)px * nf + 31) / 32) * 4 : (unsigned long long)px * nf;
         CB_TRY(run_frames_device(ctx, st, s, din, dout, nf, h, w, lo, hi, nullptr, nullptr, nullptr, nullptr));
@@ -661,7 +780,7 @@ int b200_canny_batch_host(b200_ctx* ctx, const uint8_t* frames, int n_frames, in
             // keep n_slots chunks in flight on the GPU; expand the oldest one while they run
             if (c >= n_slots - 1) CB_TRY(finish_chunk(c - (n_slots - 1)));
         } else {
-            CB_CUDA(cudaMemcpyAsync(edges + (long long)f0 * px, dout, (size_t)px * nf, cudaMemcpyDeviceToHost, st));
+            CB_CUDA(cudaMemcpyAsync(edges8 + (long long)f0 * px, dout, (size_t)px * nf, cudaMemcpyDeviceToHost, st));
         }
     }
     if (packed)
@@ -671,7 +790,25 @@ int b200_canny_batch_host(b200_ctx* ctx, const uint8_t* frames, int n_frames, in
         CB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[s], 0));
     }
     CB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int s = 0; s < 3; ++s) ctx->in_busy[s] = false;   // everything issued above has completed
     return B200_OK;
+}
+
+static bool packed_transfer_off() {
+    static const bool off = [] { const char* e = getenv("B200_CANNY_NO_PACKED_D2H"); return e && e[0] == '1'; }();
+    return off;
+}
+
+int b200_canny_batch_host(b200_ctx* ctx, const uint8_t* frames, int n_frames, int h, int w, float sigma, int lo, int hi,
+                          uint8_t* edges) {
+    CB_TRY(check_image(frames, edges, h, w));
+    if (n_frames <= 0) { set_error("n_frames must be positive"); return B200_ERR_INVALID_ARG; }
+    CB_TRY(resolve_ctx(ctx));
+    CB_TRY(prepare_gauss(ctx, sigma));
+    const long long total = (long long)n_frames * h * w;
+    // small jobs are latency-bound: the byte map goes back directly (no pack kernel, no host pass)
+    const bool packed = !packed_transfer_off() && total >= (8LL << 20);
+    return batch_host_impl(ctx, frames, n_frames, h, w, lo, hi, edges, nullptr, packed);
 }
 
 int b200_profile_stages_device(b200_ctx* ctx, const uint8_t* d_frames, int n_frames, int h, int w, float sigma, int lo, int hi,

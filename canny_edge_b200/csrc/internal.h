@@ -94,7 +94,7 @@ struct HystParams {
     unsigned int* done;          // blocks of the link kernel that have finished (zeroed with the count)
 };
 
-struct UnpackPool;  // api.cu
+struct HostPool;  // api.cu
 
 // ---- the context ------------------------------------------------------------------------------
 struct Workspace {
@@ -130,7 +130,10 @@ struct b200_ctx {
     cb::Workspace dev_in[3], dev_out[3];  // device staging for the batch_host pipeline
     cb::Workspace dev_bits[3], host_bits[3];  // bit-packed edge maps of a chunk: device side and pinned host side
     cudaEvent_t ev_chunk[3] = {nullptr, nullptr, nullptr};  // "chunk's packed map has arrived in host_bits[slot]"
-    cb::UnpackPool* pool = nullptr;       // host threads that expand the packed maps into the caller's byte buffer
+    cb::HostPool* pool = nullptr;         // host threads that expand the packed maps into the caller's buffer and stage pageable memory
+    cb::Workspace host_in[3];             // pinned staging for PAGEABLE caller frames, per pipeline slot
+    cudaEvent_t ev_in[3] = {nullptr, nullptr, nullptr};     // "the H2D copy out of host_in[slot] is done"
+    bool in_busy[3] = {false, false, false};                // ev_in[slot] has been recorded and not waited for yet
     cb::Workspace ws_band_parent;         // union-find slots of the resident band (row-band sharding)
     cb::Workspace ws_band_aux;            // boundary roots of the resident band + the cross-band forest
     int chunk_frames = 0;

@@ -34,7 +34,7 @@ def test_gray_formula_is_opencvs():
 def test_canny_bgr_matches_cvtcolor_plus_oracle(gpu_ctx, oracle):
     cv2 = pytest.importorskip("cv2")
     rng = np.random.default_rng(3)
-    for h, w in ((64, 64), (241, 322), (480, 641)):
+    for h, w in ((64, 64), (241, 322), (480, 641), (3301, 3403)):   # the last one (>= 32 MB of BGR) takes the staged / bit-packed host path
         gray0 = cb.synth_host(1, h, w, kind=0, seed=h)[0].astype(np.int16)
         frame = np.stack([np.clip(gray0 + rng.integers(-40, 41, (h, w)), 0, 255) for _ in range(3)], axis=-1).astype(np.uint8)
         edges, gray = cb.cuda_canny_bgr(frame, 1.4, 20, 60, return_gray=True, ctx=gpu_ctx)

@@ -381,3 +381,81 @@ def test_fuzz_fused_vs_oracle(gpu_ctx, oracle, seed):
             out = cb.canny_batch_host(np.stack([img, img[::-1].copy()]), sigma, lo, hi, ctx=gpu_ctx)
             assert_same("batch[0]", out[0].astype(np.int16), want)
             assert_same("batch[1]", out[1].astype(np.int16), oracle.canny(img[::-1].copy(), sigma, lo, hi))
+
+
+def test_host_paths_pageable_pinned_and_misaligned(oracle):
+    """Host entry points on pageable, misaligned and pinned buffers, one and several chunks, pixel counts that are not multiples
+    of 8 (small and medium frames: plain copies or the bit-packed return path)."""
+    import ctypes as C
+    from canny_edge_b200._lib import check, load
+    lib = load()
+    ctx = cb.Context(0)
+    try:
+        for h, w in ((300, 400), (601, 701), (1080, 1920)):
+            px = h * w
+            frames = cb.synth_host(3, h, w, kind=0, seed=7 + h)
+            want = [oracle.canny(frames[f], 1.4, 20, 60) for f in range(3)]
+            # pageable numpy memory: int16 single-frame call, byte batch call (one chunk and one frame per chunk)
+            assert_same(f"b200_canny pageable {h}x{w}", cb.cuda_canny(frames[0], 1.4, 20, 60, ctx=ctx), want[0])
+            for chunk in (0, 1):
+                ctx.set_chunk_frames(chunk)
+                out = cb.canny_batch_host(frames, 1.4, 20, 60, ctx=ctx)
+                for f in range(3):
+                    assert_same(f"batch_host pageable {h}x{w} chunk={chunk} frame {f}", out[f].astype(np.int16), want[f])
+            ctx.set_chunk_frames(0)
+            # misaligned pageable output buffers (offset by 1 element) and a misaligned input
+            raw8 = np.empty(3 * px + 1, np.uint8)
+            out8 = raw8[1:].reshape(3, h, w)
+            rawi = np.empty(3 * px + 3, np.uint8)
+            rawi[3:] = frames.reshape(-1)
+            check(lib.b200_canny_batch_host(ctx.handle, rawi[3:].ctypes.data, 3, h, w, C.c_float(1.4), 20, 60, out8.ctypes.data))
+            for f in range(3):
+                assert_same(f"misaligned u8 {h}x{w} frame {f}", out8[f].astype(np.int16), want[f])
+            raw16 = np.empty(px + 1, np.int16)
+            out16 = raw16[1:].reshape(h, w)
+            check(lib.b200_canny(ctx.handle, frames[1].ctypes.data, C.c_float(1.4), 20, 60, h, w, out16.ctypes.data))
+            assert_same(f"misaligned i16 {h}x{w}", out16, want[1])
+            # pinned buffers allocated through the library
+            pin = [C.c_void_p() for _ in range(3)]
+            for p_, nbytes in zip(pin, (3 * px, 3 * px, 2 * px)):
+                check(lib.b200_host_alloc_pinned(nbytes, C.byref(p_)))
+            try:
+                C.memmove(pin[0], frames.ctypes.data, 3 * px)
+                check(lib.b200_canny_batch_host(ctx.handle, pin[0], 3, h, w, C.c_float(1.4), 20, 60, pin[1]))
+                got = np.ctypeslib.as_array(C.cast(pin[1], C.POINTER(C.c_uint8)), shape=(3, h, w))
+                for f in range(3):
+                    assert_same(f"batch_host pinned {h}x{w} frame {f}", got[f].astype(np.int16), want[f])
+                check(lib.b200_canny(ctx.handle, pin[0], C.c_float(1.4), 20, 60, h, w, pin[2]))
+                got16 = np.ctypeslib.as_array(C.cast(pin[2], C.POINTER(C.c_int16)), shape=(h, w))
+                assert_same(f"b200_canny pinned {h}x{w}", got16, want[0])
+            finally:
+                for p_ in pin:
+                    check(lib.b200_host_free_pinned(p_))
+    finally:
+        ctx.set_chunk_frames(0)
+        ctx.close()
+
+
+def test_large_pageable_frames_take_the_staged_path(oracle):
+    """Jobs of >= 32 MB in PAGEABLE memory are staged through pinned memory by the host thread pool and come back bit-packed,
+    expanded to bytes or to the reference's int16 on the host: one 33.6 Mpix frame through b200_canny (int16, misaligned output,
+    pixel count not a multiple of 8) and a five-frame 4K batch through b200_canny_batch_host, against the oracle."""
+    import ctypes as C
+    from canny_edge_b200._lib import check, load
+    lib = load()
+    ctx = cb.Context(0)
+    try:
+        h, w = 5999, 5601
+        img = cb.synth_host(1, h, w, kind=0, seed=5)[0]
+        want = oracle.canny(img, 1.4, 20, 60)
+        assert_same("b200_canny staged", cb.cuda_canny(img, 1.4, 20, 60, ctx=ctx), want)
+        raw16 = np.empty(h * w + 1, np.int16)
+        out16 = raw16[1:].reshape(h, w)
+        check(lib.b200_canny(ctx.handle, img.ctypes.data, C.c_float(1.4), 20, 60, h, w, out16.ctypes.data))
+        assert_same("b200_canny staged, misaligned output", out16, want)
+        frames = cb.synth_host(5, 2160, 3840, kind=0, seed=77)
+        out = cb.canny_batch_host(frames, 1.4, 20, 60, ctx=ctx)
+        for f in (0, 2, 4):
+            assert_same(f"batch_host staged frame {f}", out[f].astype(np.int16), oracle.canny(frames[f], 1.4, 20, 60))
+    finally:
+        ctx.close()

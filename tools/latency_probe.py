@@ -30,8 +30,21 @@ for name, h, w, sigma in (("1080p_sigma1.4", 1080, 1920, 1.4), ("4k_sigma1.4", 2
     def host_u8_call():
         check(lib.b200_canny_batch_host(ctx.handle, img.ctypes.data, 1, h, w, C.c_float(sigma), 20, 60, e8.ctypes.data))
 
+    # the same two calls on pinned host buffers (what a capture pipeline that allocates its frames through the library gets)
+    pin = [C.c_void_p() for _ in range(3)]
+    for p_, nbytes in zip(pin, (h * w, h * w, 2 * h * w)):
+        check(lib.b200_host_alloc_pinned(nbytes, C.byref(p_)))
+    C.memmove(pin[0], img.ctypes.data, h * w)
+
+    def host_u8_pinned():
+        check(lib.b200_canny_batch_host(ctx.handle, pin[0], 1, h, w, C.c_float(sigma), 20, 60, pin[1]))
+
+    def host_i16_pinned():
+        check(lib.b200_canny(ctx.handle, pin[0], C.c_float(sigma), 20, 60, h, w, pin[2]))
+
     res = {}
-    for label, fn in (("b200_canny_host_i16_ms", host_call), ("b200_canny_batch_host_u8_ms", host_u8_call)):
+    for label, fn in (("b200_canny_host_i16_ms", host_call), ("b200_canny_batch_host_u8_ms", host_u8_call),
+                      ("b200_canny_host_i16_pinned_ms", host_i16_pinned), ("b200_canny_batch_host_u8_pinned_ms", host_u8_pinned)):
         for _ in range(3):
             fn()
         ts = []
@@ -58,5 +71,7 @@ for name, h, w, sigma in (("1080p_sigma1.4", 1080, 1920, 1.4), ("4k_sigma1.4", 2
     res["device_resident_Mpix_s"] = round(h * w / res["device_resident_ms"] / 1e3, 1)
     ctx.set_stream(0)
     torch.cuda.set_stream(torch.cuda.default_stream())
+    for p_ in pin:
+        check(lib.b200_host_free_pinned(p_))
     out[name] = res
 print(json.dumps(out))

@@ -243,6 +243,9 @@ static HostPool* get_pool(b200_ctx* ctx) {
         int local_world = 1;
         if (const char* e = getenv("LOCAL_WORLD_SIZE")) local_world = std::max(1, atoi(e));
         int n_threads = (int)std::min<unsigned>(std::max<unsigned>((hc ? hc : 4) / (2u * (unsigned)local_world), 1), 4) - 1;
+        // eight processes saturate the host's memory system with 2 threads each however many cores there are (a later 8-GPU bench
+        // run on a host with more vCPUs, 4 threads per rank by the rule above, reproduced the 87 Gpix/s of the 4-thread probe)
+        if (local_world >= 8) n_threads = std::min(n_threads, 1);
         if (const char* e = getenv("B200_CANNY_UNPACK_THREADS")) n_threads = std::max(0, atoi(e) - 1);
         ctx->pool = new HostPool(std::max(0, n_threads));
     }

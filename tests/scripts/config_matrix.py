@@ -8,7 +8,7 @@ finishes in reasonable time:
 
 Not collected by pytest (no test_ prefix): it is a measurement script that lives under tests/ because it drives the oracle.
 
-    python tests/config_matrix.py [--skip-c5-ref] [--out gpurun_out/config_matrix.json]
+    python tests/scripts/config_matrix.py [--skip-c5-ref] [--out gpurun_out/config_matrix.json]
 """
 import argparse
 import ctypes as C
@@ -19,7 +19,7 @@ from pathlib import Path
 
 import numpy as np
 
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 import torch  # noqa: E402
 

@@ -2,7 +2,7 @@
 rank 0 and compared bit for bit with the CPU oracle on the whole image.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        tests/multigpu_bands_check.py --height 4096 --width 4096 --kind 1
+        tests/scripts/multigpu_bands_check.py --height 4096 --width 4096 --kind 1
 """
 import argparse
 import ctypes as C
@@ -11,7 +11,7 @@ import os
 import sys
 from pathlib import Path
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 
 import numpy as np  # noqa: E402

@@ -3,7 +3,7 @@ right edge), a batch through both hysteresis families, and a 3-band virtual band
 import sys
 from pathlib import Path
 
-sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
 import numpy as np  # noqa: E402
 
 import canny_edge_b200 as cb  # noqa: E402

@@ -1,6 +1,10 @@
+"""Debug aid: runs one synthetic frame through b200_canny_steps and the oracle and reports, per stage plane, where they differ.
+
+    python tests/scripts/stage_mismatch_report.py HEIGHT WIDTH SIGMA
+"""
 import sys, os
 from pathlib import Path
-sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
 import numpy as np
 import canny_edge_b200 as cb
 from oracle.bindings import Oracle

@@ -66,7 +66,7 @@ def test_bands_over_nccl_two_gpus():
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    script = Path(__file__).resolve().parent / "multigpu_bands_check.py"
+    script = Path(__file__).resolve().parent / "scripts" / "multigpu_bands_check.py"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29533", str(script), "--height", "2048", "--width", "2048", "--kind", "1"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)

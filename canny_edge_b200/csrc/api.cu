@@ -62,6 +62,13 @@ int ensure_ws(Workspace& ws, size_t bytes, bool pinned_host) {
         return B200_ERR_NOMEM;
     }
     ws.bytes = want;
+    if (!pinned_host) {
+        // the head of a fresh device workspace is zero: the weak-pixel lists keep their counter block there (HystParams::ctr).
+        // Synchronous on purpose (allocation is rare): the context's streams do not order themselves after the null stream.
+        e = cudaMemset(ws.ptr, 0, 64);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+        if (e != cudaSuccess) { set_error("workspace initialisation failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return B200_ERR_CUDA; }
+    }
     return B200_OK;
 }
 
@@ -322,24 +329,30 @@ static int run_frames_device(b200_ctx* ctx, cudaStream_t st, int slot, const uin
     fp.parent = reinterpret_cast<int32_t*>(ctx->ws_parent[slot].ptr);
     fp.kept_count = reinterpret_cast<unsigned int*>(ctx->ws_list[slot].ptr);
     fp.kept_list = reinterpret_cast<uint32_t*>(ctx->ws_list[slot].ptr) + 16;
-    CB_CUDA(cudaMemsetAsync(fp.kept_count, 0, 2 * sizeof(unsigned int), st));   // list length + link-kernel block counter
+    // the list's counter block is zero here: zeroed at allocation and retired by the previous launch's kernels (HystParams::ctr);
+    // only a launch that failed half-way leaves it dirty
+    if (ctx->list_dirty[slot]) CB_CUDA(cudaMemsetAsync(fp.kept_count, 0, 64, st));
+    ctx->list_dirty[slot] = true;
     bool sparse = false;
     CB_TRY(launch_front(ctx, st, fp, &sparse));
     static const long long dense_div = [] { const char* e = getenv("B200_CANNY_DENSE_DIV"); return e ? atoll(e) : 8LL; }();
-    const bool dense = ctx->kept_px[slot] > 0 && (long long)ctx->h_kept[slot] * dense_div > ctx->kept_px[slot];   // previous launch of this slot
-    if (sparse) {
-        CB_CUDA(cudaMemcpyAsync(&ctx->h_kept[slot], fp.kept_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-        ctx->kept_px[slot] = (long long)nf * px;
-    }
+    // weak-pixel count of the previous launch of this slot (written into mapped pinned memory by its kernels, never waited for)
+    const unsigned int prev_kept = *reinterpret_cast<volatile unsigned int*>(&ctx->h_kept[slot]);
+    const bool dense = ctx->kept_px[slot] > 0 && (long long)prev_kept * dense_div > ctx->kept_px[slot];
+    if (sparse) ctx->kept_px[slot] = (long long)nf * px;
+    const long long thresh = (long long)nf * px / dense_div;   // n * dense_div > px  <=>  n > floor(px / dense_div)
     HystParams hp;
     memset(&hp, 0, sizeof(hp));
     hp.cls = d_out;
     hp.list = (sparse && !dense) ? fp.kept_list : nullptr;
-    hp.count = fp.kept_count;
-    hp.done = fp.kept_count + 1;
+    hp.ctr = sparse ? fp.kept_count : nullptr;
+    hp.h_kept = ctx->d_kept + slot;
+    hp.kept_prev = prev_kept;
+    hp.kept_thresh = (unsigned int)std::min<long long>(thresh, 0xffffffffLL);
     hp.parent = reinterpret_cast<int32_t*>(ctx->ws_parent[slot].ptr);
     hp.frame_stride = px; hp.rows = h; hp.width = w; hp.row0 = 0; hp.n_frames = nf;
     CB_TRY(launch_hysteresis(ctx, st, hp));
+    ctx->list_dirty[slot] = false;
     return B200_OK;
 }
 
@@ -398,8 +411,9 @@ int b200_ctx_create(int device, b200_ctx** out) {
             CB_CUDA(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
         }
         CB_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-        CB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_kept), 4 * sizeof(unsigned int)));
+        CB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&c->h_kept), 4 * sizeof(unsigned int), cudaHostAllocMapped));
         memset(c->h_kept, 0, 4 * sizeof(unsigned int));
+        CB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->d_kept), c->h_kept, 0));
         return B200_OK;
     };
     const int rc = init();
@@ -694,7 +708,11 @@ int b200_canny_batch_device(b200_ctx* ctx, const uint8_t* d_frames, int n_frames
     const long long px = (long long)h * w;
     const int chunk = auto_chunk_frames(ctx, h, w, n_frames);
     const int n_chunks = (n_frames + chunk - 1) / chunk;
-    const int n_slots = n_chunks >= 2 ? 2 : 1;
+    // three slots: while one chunk's small, latency-bound hysteresis kernels wait for SM resources, the front kernels of the TWO
+    // following chunks are already queued on their own streams, so the machine never waits for a front kernel that is itself
+    // waiting (same slot) for those hysteresis kernels (226 against 219 Gpix/s with two slots; running the hysteresis kernels on
+    // high-priority streams on top of that measured 222)
+    const int n_slots = std::min(3, n_chunks);
     for (int s = 0; s < n_slots; ++s) {
         CB_TRY(ensure_ws(ctx->ws_parent[s], (size_t)px * 4 * (size_t)chunk));
         CB_TRY(ensure_ws(ctx->ws_list[s], list_bytes(chunk, h, w)));
@@ -703,7 +721,7 @@ int b200_canny_batch_device(b200_ctx* ctx, const uint8_t* d_frames, int n_frames
         CB_TRY(run_frames_device(ctx, ctx->stream, 0, d_frames, d_edges, n_frames, h, w, lo, hi, nullptr, nullptr, nullptr, nullptr));
         return B200_OK;
     }
-    // two side streams take alternate chunks so one chunk's tail waves overlap the next chunk's head
+    // the side streams take the chunks in turn so one chunk's tail waves overlap the next chunks' heads
     CB_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
     for (int s = 0; s < n_slots; ++s) CB_CUDA(cudaStreamWaitEvent(ctx->side[s], ctx->ev_fork, 0));
     for (int c = 0; c < n_chunks; ++c) {

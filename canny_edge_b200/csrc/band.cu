@@ -170,24 +170,28 @@ int b200_band_front(b200_ctx* ctx, const uint8_t* d_rows, int halo_above, int ha
     fp.parent = reinterpret_cast<int32_t*>(ctx->ws_band_parent.ptr);
     fp.kept_count = reinterpret_cast<unsigned int*>(ctx->ws_band_list.ptr);
     fp.kept_list = reinterpret_cast<uint32_t*>(ctx->ws_band_list.ptr) + 16;
-    CB_CUDA(cudaMemsetAsync(fp.kept_count, 0, 2 * sizeof(unsigned int), st));   // list length + link-kernel block counter
+    // the list's counter block is zero here (zeroed at allocation, retired by the previous band's kernels: HystParams::ctr)
+    if (ctx->list_dirty[3]) CB_CUDA(cudaMemsetAsync(fp.kept_count, 0, 64, st));
+    ctx->list_dirty[3] = true;
     bool sparse = false;
     CB_TRY(launch_front(ctx, st, fp, &sparse));
-    const bool dense = ctx->kept_px[3] > 0 && (long long)ctx->h_kept[3] * 8 > ctx->kept_px[3];   // previous band on this context
-    if (sparse) {
-        CB_CUDA(cudaMemcpyAsync(&ctx->h_kept[3], fp.kept_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-        ctx->kept_px[3] = px;
-    }
+    const unsigned int prev_kept = *reinterpret_cast<volatile unsigned int*>(&ctx->h_kept[3]);   // previous band on this context
+    const bool dense = ctx->kept_px[3] > 0 && (long long)prev_kept * 8 > ctx->kept_px[3];
+    if (sparse) ctx->kept_px[3] = px;
+    const bool front_sparse = sparse;
     sparse = sparse && !dense;
     ctx->band_sparse = sparse;
     HystParams hp;
     memset(&hp, 0, sizeof(hp));
     hp.list = sparse ? fp.kept_list : nullptr;
-    hp.count = fp.kept_count;
-    hp.done = fp.kept_count + 1;
+    hp.ctr = front_sparse ? fp.kept_count : nullptr;
+    hp.h_kept = ctx->d_kept + 3;
+    hp.kept_prev = prev_kept;
+    hp.kept_thresh = (unsigned int)(px / 8);
     hp.cls = d_edges; hp.parent = reinterpret_cast<int32_t*>(ctx->ws_band_parent.ptr);
     hp.frame_stride = px; hp.rows = band_rows; hp.width = width; hp.row0 = row0; hp.n_frames = 1;
     CB_TRY(launch_ccl_label(ctx, st, hp));
+    ctx->list_dirty[3] = false;
     ctx->band_rows = band_rows; ctx->band_width = width; ctx->band_row0 = row0; ctx->band_cls = d_edges;
     return B200_OK;
 }
@@ -257,8 +261,7 @@ int b200_band_finalize(b200_ctx* ctx, const b200_band_record* d_all, int n_bands
     memset(&hp, 0, sizeof(hp));
     hp.cls = d_edges; hp.parent = parent;
     hp.list = ctx->band_sparse ? reinterpret_cast<const uint32_t*>(ctx->ws_band_list.ptr) + 16 : nullptr;
-    hp.count = reinterpret_cast<const unsigned int*>(ctx->ws_band_list.ptr);
-    hp.done = reinterpret_cast<unsigned int*>(ctx->ws_band_list.ptr) + 1;
+    hp.ctr = reinterpret_cast<unsigned int*>(ctx->ws_band_list.ptr);   // the resolve kernel reads the retired count, ctr[2]
     hp.frame_stride = (long long)band_rows * width; hp.rows = band_rows; hp.width = width; hp.row0 = ctx->band_row0; hp.n_frames = 1;
     CB_TRY(launch_ccl_resolve(ctx, st, hp));
     return B200_OK;

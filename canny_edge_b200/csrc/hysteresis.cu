@@ -257,10 +257,10 @@ ccl_final_kernel(const HystParams p) {
 // neighbour hangs the pixel's component under SUPER; weak "forward" neighbours E, S (or SW / SE when S is not weak: with S weak
 // the two diagonals reach the pixel through S's own links) are united with it, so every weak-weak pair is visited exactly once,
 // from its earlier endpoint in raster order.  The pair (0,1)-(1,0) of the GLOBAL image is skipped in both directions (see the
-// file header): the one-way link is applied in the resolve kernel.
+// file header): the one-way link is applied by the last block of this kernel, below.
 __global__ void __launch_bounds__(256)
 ccl_sparse_link_kernel(const HystParams p) {
-    const unsigned int n = *p.count;
+    const unsigned int n = p.ctr[0];
     const int W = p.width, Hh = p.rows;
     const unsigned int fs = (unsigned int)p.frame_stride;
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -293,28 +293,45 @@ ccl_sparse_link_kernel(const HystParams p) {
     // The reference's one-way link (0,1) -> (1,0) (src/utils.cpp:399): once EVERY block has finished its unions the forest is
     // final, and the last block to get here hangs (1,0)'s component under SUPER when (0,1) is strong or strong-connected.  The
     // class bytes are still untouched at this point (the resolve kernel runs after this one).
-    if (p.row0 != 0 || Hh < 2 || W < 2) return;
     __shared__ bool s_last;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        s_last = atomicAdd(p.done, 1u) == gridDim.x - 1;
+        s_last = atomicAdd(p.ctr + 1, 1u) == gridDim.x - 1;
     }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    for (int f = threadIdx.x; f < p.n_frames; f += blockDim.x) {
-        const unsigned int f0 = (unsigned int)f * fs;
-        const int c01 = p.cls[f0 + 1], c10 = p.cls[f0 + W];
-        if (c10 == 1 && (c01 == 255 || (c01 == 1 && g_find_halve(p.parent, (int)f0 + 1) == kSuper)))
-            g_union_halve(p.parent, (int)f0 + W, kSuper);
+    if (p.row0 == 0 && Hh >= 2 && W >= 2) {
+        for (int f = threadIdx.x; f < p.n_frames; f += blockDim.x) {
+            const unsigned int f0 = (unsigned int)f * fs;
+            const int c01 = p.cls[f0 + 1], c10 = p.cls[f0 + W];
+            if (c10 == 1 && (c01 == 255 || (c01 == 1 && g_find_halve(p.parent, (int)f0 + 1) == kSuper)))
+                g_union_halve(p.parent, (int)f0 + W, kSuper);
+        }
     }
+    // every block has read ctr[0] by now: retire the counters (see HystParams::ctr)
+    if (threadIdx.x == 0) {
+        p.ctr[2] = n;
+        if (p.h_kept && ((n > p.kept_thresh) != (p.kept_prev > p.kept_thresh))) *p.h_kept = n;
+        p.ctr[0] = 0;
+        p.ctr[1] = 0;
+    }
+}
+
+// tile-based path after a front kernel that built a list nobody walks: publish and reset the counters all the same
+__global__ void list_retire_kernel(unsigned int* ctr, unsigned int* h_kept, unsigned int kept_prev, unsigned int kept_thresh) {
+    const unsigned int n = ctr[0];
+    ctr[2] = n;
+    if (h_kept && ((n > kept_thresh) != (kept_prev > kept_thresh))) *h_kept = n;
+    ctr[0] = 0;
+    ctr[1] = 0;
 }
 
 // every weak pixel chases its root: 255 when the component hangs under SUPER, else 0
 __global__ void __launch_bounds__(256)
 ccl_sparse_resolve_kernel(const HystParams p) {
-    const unsigned int n = *p.count;
+    const unsigned int n = p.ctr[2];
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const unsigned int g = p.list[i];
         p.cls[g] = (g_find_halve(p.parent, (int)g) == kSuper) ? 255 : 0;
@@ -332,6 +349,10 @@ int launch_ccl_label(b200_ctx* ctx, cudaStream_t st, const HystParams& p_in) {
         CB_CUDA(cudaGetLastError());
         ctx->launches++;
         return B200_OK;
+    }
+    if (p.ctr) {
+        list_retire_kernel<<<1, 1, 0, st>>>(p.ctr, p.h_kept, p.kept_prev, p.kept_thresh);
+        ctx->launches++;
     }
     p.tiles_x = (p.width + kTile - 1) / kTile;
     p.tiles_y = (p.rows + kTile - 1) / kTile;

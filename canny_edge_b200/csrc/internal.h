@@ -77,7 +77,7 @@ struct FrontParams {
     int32_t* parent;        // union-find slots, indexed like cls: every WEAK pixel is initialised to its own launch-relative index
                             // frame*out_frame_stride + pixel (strong pixels need no slot: they are final)
     uint32_t* kept_list;    // launch-relative indices of all weak pixels, in no particular order
-    unsigned int* kept_count;  // number of entries (zeroed by the host before the launch)
+    unsigned int* kept_count;  // number of entries: word 0 of the list's counter block (see HystParams::ctr); zero at launch
 };
 
 // ---- parameters of the hysteresis (connected components) kernels ---------------------------------
@@ -90,8 +90,18 @@ struct HystParams {
     int n_frames;
     int tiles_x, tiles_y;
     const uint32_t* list;        // weak-pixel list written by front2 (null -> tile-based labelling over the whole plane);
-    const unsigned int* count;   // the list-driven kernels keep LAUNCH-relative indices (frame*frame_stride + pixel) in parent[]
-    unsigned int* done;          // blocks of the link kernel that have finished (zeroed with the count)
+                                 // the list-driven kernels keep LAUNCH-relative indices (frame*frame_stride + pixel) in parent[]
+    // Counter block of the list (null when the front kernel did not produce one).  It is zeroed ONCE, when the workspace is
+    // allocated, and then kept consistent by the kernels themselves, so a launch needs neither a memset before the front kernel
+    // nor a copy after it:
+    //   ctr[0]  live entry count (front2's atomicAdd)        ctr[1]  link-kernel blocks that have finished
+    //   ctr[2]  entry count of the finished launch: written, with h_kept, by the last block of the link kernel (or by
+    //           list_retire_kernel on the tile-based path), which also zeroes ctr[0] and ctr[1] for the next launch
+    unsigned int* ctr;
+    unsigned int* h_kept;        // mapped pinned host word that receives the entry count (density of the next launch's choice) ...
+    unsigned int kept_prev, kept_thresh;   // ... but only when it moves across the threshold: the host's last view of it and the
+                                           // "tile-based labelling above this many weak pixels" bound (a write to host memory at the
+                                           // end of every launch measured 1 % of the batch throughput)
 };
 
 struct HostPool;  // api.cu
@@ -147,7 +157,9 @@ struct b200_ctx {
     // weak-pixel count of the last launch of each pipeline slot, copied back asynchronously (pinned host memory, never waited
     // for): when more than 1/8 of the previous launch's pixels were weak the next one uses the tile-based labelling, whose shared-
     // memory unions win on such maps.  Both give identical results; a stale value only costs speed.
-    unsigned int* h_kept = nullptr;       // [4]: slots 0..2 + the band
+    unsigned int* h_kept = nullptr;       // [4]: slots 0..2 + the band (mapped pinned memory: the kernels write it directly)
+    unsigned int* d_kept = nullptr;       // device-side address of h_kept
+    bool list_dirty[4] = {false, false, false, false};   // a launch on this slot failed between front and link: re-zero its counters
     long long kept_px[4] = {0, 0, 0, 0};
 };
 

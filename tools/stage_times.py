@@ -1,5 +1,5 @@
 """Per-kernel timing of the pipeline on synthetic frames resident in HBM (CUDA events around every
-kernel, serial on one stream) + whole-pipeline throughput with the two-stream chunk overlap.
+kernel, serial on one stream) + whole-pipeline throughput with the three-stream chunk overlap.
 
     python tools/stage_times.py --frames 64 --height 2160 --width 3840 --sigma 1.4 --kind 0
 """

@@ -72,6 +72,8 @@ SIGNATURES = {
     "b200_division_check_device": (C.c_int, [_ctx, C.c_float, C.POINTER(C.c_ulonglong)]),
     "b200_division_mode_device": (C.c_int, [_ctx, C.c_float, C.POINTER(C.c_int)]),
     "b200_count_edges_device": (C.c_int, [_ctx, _u8p, C.c_size_t, C.POINTER(C.c_ulonglong)]),
+    "b200_pack_edges_device": (C.c_int, [_ctx, _u8p, C.c_size_t, C.c_void_p]),
+    "b200_unpack_edges_host": (C.c_int, [_u8p, C.c_size_t, C.c_void_p, C.c_int, C.c_int]),
     "b200_device_alloc": (C.c_int, [_ctx, C.c_size_t, C.POINTER(C.c_void_p)]),
     "b200_device_free": (C.c_int, [_ctx, C.c_void_p]),
     "b200_memcpy_h2d": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_size_t]),

@@ -832,6 +832,24 @@ int b200_canny_batch_host(b200_ctx* ctx, const uint8_t* frames, int n_frames, in
     return batch_host_impl(ctx, frames, n_frames, h, w, lo, hi, edges, nullptr, packed);
 }
 
+int b200_pack_edges_device(b200_ctx* ctx, const uint8_t* d_edges, size_t n_px, uint32_t* d_bits) {
+    if (!d_edges || !d_bits || n_px == 0) { set_error("bad argument to b200_pack_edges_device"); return B200_ERR_INVALID_ARG; }
+    CB_TRY(resolve_ctx(ctx));
+    return launch_pack_edges(ctx, ctx->stream, d_edges, d_bits, n_px);
+}
+
+int b200_unpack_edges_host(const uint8_t* bits, size_t n_px, void* out, int elem_size, int threads) {
+    if (!bits || !out || (elem_size != 1 && elem_size != 2)) { set_error("bad argument to b200_unpack_edges_host"); return B200_ERR_INVALID_ARG; }
+    if (n_px == 0) return B200_OK;
+    if (threads <= 0) {
+        const unsigned hc = std::thread::hardware_concurrency();
+        threads = (int)std::min<unsigned>(std::max<unsigned>((hc ? hc : 4) / 2u, 1), 4);
+    }
+    HostPool pool(std::min(threads, 64) - 1);   // short-lived: this entry point has no context to keep one in
+    pool.run(elem_size == 1 ? HostPool::kUnpackU8 : HostPool::kUnpackI16, bits, out, n_px);
+    return B200_OK;
+}
+
 int b200_profile_stages_device(b200_ctx* ctx, const uint8_t* d_frames, int n_frames, int h, int w, float sigma, int lo, int hi,
                                uint8_t* d_edges, float* ms_out, int* launches_out) {
     CB_TRY(check_image(d_frames, d_edges, h, w));

@@ -148,8 +148,9 @@ int b200_bgr_to_gray_device(b200_ctx* ctx, const uint8_t* d_bgr, size_t n_px, ui
 /* n_frames independent frames, host memory in, host memory out (u8, 0/255).  What main.cpp's frame
  * loop (src/main.cpp:120-137) becomes for N frames: chunked, H2D / kernels / D2H overlapped on
  * separate streams.  frames: n_frames*height*width bytes.  Pinned (page-locked) buffers give the full
- * PCIe rate; pageable ones work.  Jobs of >= 8 Mpix return the map over PCIe bit-packed and expand it
- * into `edges` with a few host threads while the GPU works on the next chunk. */
+ * PCIe rate; pageable ones work (jobs of >= 32 MB are staged through pinned memory by the library's host
+ * threads).  Jobs of >= 8 Mpix return the map over PCIe bit-packed and expand it into `edges` with a few
+ * host threads while the GPU works on the next chunk. */
 int b200_canny_batch_host(b200_ctx* ctx, const uint8_t* frames, int n_frames, int height, int width,
                           float sigma, int min_val, int max_val, uint8_t* edges);
 
@@ -158,6 +159,16 @@ int b200_canny_batch_host(b200_ctx* ctx, const uint8_t* frames, int n_frames, in
  * d_frames. */
 int b200_canny_batch_device(b200_ctx* ctx, const uint8_t* d_frames, int n_frames, int height,
                             int width, float sigma, int min_val, int max_val, uint8_t* d_edges);
+
+/* The packed form of an edge map — 1 bit per pixel, bit i of byte k <-> pixel 8k+i, ceil(n_px/32)*4 bytes — is what
+ * b200_canny_batch_host moves over PCIe.  Both halves are exported for callers that store or ship maps in that form:
+ *   b200_pack_edges_device   0 / 255 bytes in DEVICE memory -> packed words in DEVICE memory, asynchronous on the context's
+ *                            stream (d_bits: ceil(n_px/32) 32-bit words);
+ *   b200_unpack_edges_host   packed bytes in HOST memory -> 0 / 255 values in HOST memory, as bytes (elem_size 1) or as the
+ *                            reference's int16 (elem_size 2), on `threads` host threads (<= 0: the library's default).  Pure
+ *                            host code: needs no GPU.  (No reference counterpart: src/utils.cpp:322-342 writes int16 in place.) */
+int b200_pack_edges_device(b200_ctx* ctx, const uint8_t* d_edges, size_t n_px, uint32_t* d_bits);
+int b200_unpack_edges_host(const uint8_t* bits, size_t n_px, void* out, int elem_size, int threads);
 
 /* The same work as b200_canny_batch_device, issued serially on the context's stream with a CUDA event
  * pair around every kernel; blocks, then returns per-kernel-class totals: ms_out[5] / launches_out[5]

@@ -95,3 +95,24 @@ def test_argument_validation_without_device():
     o = np.zeros((1, 8), np.int16)
     # height < 2 is rejected before any device work (the reference reads out of bounds there)
     assert lib.b200_gaussian(None, z.ctypes.data, C.c_float(1.4), 1, 8, o.ctypes.data) == _lib.ERR_INVALID_ARG
+
+
+def test_unpack_edges_host_matches_numpy():
+    """The host half of the bit-packed edge transfer (pure host code, thread pool + streaming stores): against numpy's
+    unpackbits for byte and int16 output, one and several threads, aligned and misaligned outputs, pixel counts that are not
+    multiples of 8 / 64, sizes on both sides of the single-thread shortcut."""
+    lib = _lib.load()
+    rng = np.random.default_rng(11)
+    for n_px in (1, 7, 8, 63, 64, 1000, 4097, 300_001, 2_000_003):
+        bits = rng.integers(0, 256, (n_px + 7) // 8, dtype=np.uint8)
+        want = np.unpackbits(bits, bitorder="little")[:n_px].astype(np.int16) * 255
+        for threads in (1, 4, 0):
+            for elem, dt in ((1, np.uint8), (2, np.int16)):
+                for off in (0, 1):
+                    raw = np.full(n_px + 1 + 8, 77, dt)
+                    out = raw[off:off + n_px]
+                    assert lib.b200_unpack_edges_host(bits.ctypes.data, n_px, out.ctypes.data, elem, threads) == 0
+                    assert (out.astype(np.int16) == want).all(), (n_px, threads, elem, off)
+                    assert (raw[off + n_px:] == 77).all() and (raw[:off] == 77).all(), "wrote outside the output"
+    assert lib.b200_unpack_edges_host(None, 8, None, 1, 1) != 0
+    assert lib.b200_unpack_edges_host(bits.ctypes.data, 8, out.ctypes.data, 4, 1) != 0

@@ -459,3 +459,25 @@ def test_large_pageable_frames_take_the_staged_path(oracle):
             assert_same(f"batch_host staged frame {f}", out[f].astype(np.int16), oracle.canny(frames[f], 1.4, 20, 60))
     finally:
         ctx.close()
+
+
+def test_pack_edges_device_round_trip(gpu_ctx):
+    """b200_pack_edges_device (0 / 255 bytes -> 1 bit per pixel, on the GPU) and b200_unpack_edges_host are inverses, for pixel
+    counts that are not multiples of 8 or 32."""
+    import torch
+    from canny_edge_b200._lib import check, load
+    lib = load()
+    for h, w in ((270, 480), (301, 333), (1080, 1920)):
+        img = cb.synth_host(1, h, w, kind=1, seed=h)[0]
+        edges = cb.cuda_canny(img, 1.4, 20, 60, ctx=gpu_ctx).astype(np.uint8)
+        n_px = h * w
+        d_edges = torch.from_numpy(edges).cuda()
+        d_bits = torch.zeros(((n_px + 31) // 32,), dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()   # the context issues on its own stream, not on torch's
+        check(lib.b200_pack_edges_device(gpu_ctx.handle, d_edges.data_ptr(), n_px, d_bits.data_ptr()))
+        gpu_ctx.synchronize()
+        bits = d_bits.cpu().numpy().view(np.uint8)
+        assert (np.unpackbits(bits, bitorder="little")[:n_px].reshape(h, w) * 255 == edges).all()
+        out = np.empty((h, w), np.int16)
+        check(lib.b200_unpack_edges_host(bits.ctypes.data, n_px, out.ctypes.data, 2, 0))
+        assert (out == edges).all()

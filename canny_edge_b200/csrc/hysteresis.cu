@@ -14,11 +14,16 @@
 // (0,1)-(1,0) is therefore left out of the forest and re-applied one-way in the final pass: if (0,1)'s
 // component is strong, (1,0)'s becomes strong; not the other way round.
 //
-// Kernels:
-//   ccl_local   one CTA per 64x64 tile: union-find in shared memory (atomicMin links, row-run seeding
-//               with warp ballots), then writes each candidate's parent (its tile root, or SUPER).
-//   ccl_merge   one thread per pixel on a tile boundary: lock-free atomicMin unions in global memory.
-//   ccl_final   every weak pixel chases its root; rewrites the class map to 0 / 255 in place.
+// Two kernel families, identical results:
+//   list-driven (the default after front2.cu, which hands over a list of the WEAK pixels and their union-find slots):
+//     ccl_sparse_link     one thread per weak pixel: strong neighbour -> SUPER, unions with its forward weak neighbours; the
+//                         last block applies the one-way link and retires the list's counters (HystParams::ctr)
+//     ccl_sparse_resolve  every weak pixel chases its root and becomes 0 or 255
+//   tile-based (stage API, minVal <= 0, maps with more than 1/8 weak pixels):
+//     ccl_local   one CTA per 64x64 tile: union-find in shared memory (atomicMin links, row-run seeding
+//                 with warp ballots), then writes each candidate's parent (its tile root, or SUPER).
+//     ccl_merge   one thread per pixel on a tile boundary: lock-free atomicMin unions in global memory.
+//     ccl_final   every weak pixel chases its root; rewrites the class map to 0 / 255 in place.
 #include <string.h>
 
 #include "ccl.cuh"

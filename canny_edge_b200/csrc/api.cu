@@ -333,8 +333,12 @@ static int run_frames_device(b200_ctx* ctx, cudaStream_t st, int slot, const uin
     // only a launch that failed half-way leaves it dirty
     if (ctx->list_dirty[slot]) CB_CUDA(cudaMemsetAsync(fp.kept_count, 0, 64, st));
     ctx->list_dirty[slot] = true;
-    bool sparse = false;
-    CB_TRY(launch_front(ctx, st, fp, &sparse));
+    // EXPERIMENTAL (B200_CANNY_LOCAL_LINK=1, not yet validated on hardware): tile-local hysteresis linking in the front kernel
+    static const bool want_local = [] { const char* e = getenv("B200_CANNY_LOCAL_LINK"); return e && e[0] == '1'; }();
+    if (want_local && ensure_ws(ctx->ws_border[slot], ctx->ws_list[slot].bytes) == B200_OK)
+        fp.border_list = reinterpret_cast<uint32_t*>(ctx->ws_border[slot].ptr);
+    bool sparse = false, local = false;
+    CB_TRY(launch_front(ctx, st, fp, &sparse, &local));
     static const long long dense_div = [] { const char* e = getenv("B200_CANNY_DENSE_DIV"); return e ? atoll(e) : 8LL; }();
     // weak-pixel count of the previous launch of this slot (written into mapped pinned memory by its kernels, never waited for)
     const unsigned int prev_kept = *reinterpret_cast<volatile unsigned int*>(&ctx->h_kept[slot]);
@@ -345,6 +349,7 @@ static int run_frames_device(b200_ctx* ctx, cudaStream_t st, int slot, const uin
     memset(&hp, 0, sizeof(hp));
     hp.cls = d_out;
     hp.list = (sparse && !dense) ? fp.kept_list : nullptr;
+    if (hp.list && local) hp.border_list = fp.border_list;
     hp.ctr = sparse ? fp.kept_count : nullptr;
     hp.h_kept = ctx->d_kept + slot;
     hp.kept_prev = prev_kept;
@@ -430,7 +435,7 @@ int b200_ctx_destroy(b200_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     auto rel = [](Workspace& w, bool pinned) { if (w.ptr) { if (pinned) cudaFreeHost(w.ptr); else cudaFree(w.ptr); w.ptr = nullptr; w.bytes = 0; } };
-    for (int i = 0; i < 3; ++i) { rel(c->ws_parent[i], false); rel(c->ws_list[i], false); rel(c->dev_in[i], false); rel(c->dev_out[i], false); }
+    for (int i = 0; i < 3; ++i) { rel(c->ws_parent[i], false); rel(c->ws_list[i], false); rel(c->ws_border[i], false); rel(c->dev_in[i], false); rel(c->dev_out[i], false); }
     rel(c->ws_planes, false); rel(c->ws_misc, false); rel(c->ws_band_parent, false); rel(c->ws_band_list, false); rel(c->ws_band_aux, false);
     if (c->gauss.d_w) cudaFree(c->gauss.d_w);
     if (c->h_kept) cudaFreeHost(c->h_kept);

@@ -78,6 +78,9 @@ struct FrontParams {
                             // frame*out_frame_stride + pixel (strong pixels need no slot: they are final)
     uint32_t* kept_list;    // launch-relative indices of all weak pixels, in no particular order
     unsigned int* kept_count;  // number of entries: word 0 of the list's counter block (see HystParams::ctr); zero at launch
+    uint32_t* border_list;     // EXPERIMENTAL tile-local linking (front2.cu LL, local_link.cuh): when set, front2 links the weak
+                               // pixels of every tile itself, writes final tile-local roots into parent[] and lists here the weak
+                               // pixels on tile borders, the only ones the global link kernel still has to visit (count: ctr[1])
 };
 
 // ---- parameters of the hysteresis (connected components) kernels ---------------------------------
@@ -97,11 +100,14 @@ struct HystParams {
     //   ctr[0]  live entry count (front2's atomicAdd)        ctr[1]  link-kernel blocks that have finished
     //   ctr[2]  entry count of the finished launch: written, with h_kept, by the last block of the link kernel (or by
     //           list_retire_kernel on the tile-based path), which also zeroes ctr[0] and ctr[1] for the next launch
+    // (experimental tile-local linking: ctr[1] is the border list's live count instead and ctr[3] counts the finished blocks)
     unsigned int* ctr;
     unsigned int* h_kept;        // mapped pinned host word that receives the entry count (density of the next launch's choice) ...
     unsigned int kept_prev, kept_thresh;   // ... but only when it moves across the threshold: the host's last view of it and the
                                            // "tile-based labelling above this many weak pixels" bound (a write to host memory at the
                                            // end of every launch measured 1 % of the batch throughput)
+    const uint32_t* border_list; // experimental tile-local linking (front2.cu LL): when set, the link kernel walks only these weak
+                                 // pixels (count ctr[1]); `list` (count ctr[0]) is still what the resolve kernel walks
 };
 
 struct HostPool;  // api.cu
@@ -134,6 +140,7 @@ struct b200_ctx {
     cb::GaussTables gauss;
     cb::Workspace ws_parent[3];   // int32 union-find slots for one chunk, per pipeline slot
     cb::Workspace ws_list[3];     // kept-pixel lists for one chunk ([0..15] = counter block, entries from word 16), per pipeline slot
+    cb::Workspace ws_border[3];   // border-pixel lists (experimental tile-local linking), per pipeline slot
     cb::Workspace ws_band_list;   // kept-pixel list of the resident band
     cb::Workspace ws_planes;      // stage-API scratch planes
     cb::Workspace ws_misc;
@@ -186,11 +193,12 @@ int host_window(float sigma);
 
 // front.cu
 // *sparse_out (optional) tells whether the kernel that ran filled p.parent / p.kept_list
-int launch_front(b200_ctx* ctx, cudaStream_t st, const FrontParams& p, bool* sparse_out = nullptr);
+// sparse_out: the kernel produced the weak-pixel list; local_out: it also linked every tile itself and produced the border list
+int launch_front(b200_ctx* ctx, cudaStream_t st, const FrontParams& p, bool* sparse_out = nullptr, bool* local_out = nullptr);
 int make_input_tensor_map(const FrontParams& p, int box_cols, int box_rows, CUtensorMap_st* tmap, bool* use_tma);
 // front2.cu
 bool front2_supports(int radius);
-int launch_front2(b200_ctx* ctx, cudaStream_t st, const FrontParams& p);
+int launch_front2(b200_ctx* ctx, cudaStream_t st, const FrontParams& p, bool* local_out = nullptr);
 // selftest.cu
 int check_div_mode_device(b200_ctx* ctx, float b, float y, float* c, int* mode);
 // hysteresis.cu

@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "local_link.cuh"
@@ -34,12 +35,33 @@ void gunion(std::vector<int>& parent, int a, int b) {
 
 // cls: H x W bytes, 0 / 1 (weak) / 255 (strong).  out: 0 / 255.  slab_rows: class rows per tile (<= 64), row0: global row of
 // cls row 0 (the (0,1)/(1,0) rule applies to GLOBAL rows 0 and 1).  Returns the number of weak pixels the global link visited.
+// n_threads > 1: the init / link / emit phases of every tile run on that many host threads with real atomics (a join between
+// phases stands in for the kernel's barriers), so the lock-free union-find is exercised under true concurrency as well.
+extern "C" long long ll_emulate_mt(const uint8_t* cls, int H, int W, int slab_rows, int row0, uint8_t* out, int n_threads);
 extern "C" long long ll_emulate(const uint8_t* cls, int H, int W, int slab_rows, int row0, uint8_t* out) {
+    return ll_emulate_mt(cls, H, W, slab_rows, row0, out, 1);
+}
+extern "C" long long ll_emulate_mt(const uint8_t* cls, int H, int W, int slab_rows, int row0, uint8_t* out, int n_threads) {
     std::vector<int> parent((size_t)H * W, -12345);   // poison: slots of non-weak pixels must never be followed
     std::vector<int> all_list, border_list;
     std::vector<uint32_t> weak(kRows * kWords), strong(kRows * kWords);
     std::vector<int> lab(kRows * kPitch);
-    auto amin = [](int* addr, int v) { const int old = *addr; if (v < old) *addr = v; return old; };
+    auto amin = [](int* addr, int v) {
+        int old = __atomic_load_n(addr, __ATOMIC_RELAXED);
+        while (v < old && !__atomic_compare_exchange_n(addr, &old, v, false, __ATOMIC_ACQ_REL, __ATOMIC_RELAXED)) {}
+        return old;
+    };
+    // runs fn(r, k) for all 256 words of a tile, on n_threads threads (interleaved assignment, like lanes of different warps)
+    auto for_words = [&](auto fn) {
+        if (n_threads <= 1) {
+            for (int i = 0; i < kRows * kWords; ++i) fn(i / kWords, i % kWords);
+            return;
+        }
+        std::vector<std::thread> ts;
+        for (int t = 0; t < n_threads; ++t)
+            ts.emplace_back([&, t] { for (int i = t; i < kRows * kWords; i += n_threads) fn(i / kWords, i % kWords); });
+        for (auto& th : ts) th.join();
+    };
     for (int y0 = 0; y0 < H; y0 += slab_rows) {
         const int rows = std::min(slab_rows, H - y0);
         for (int x0 = 0; x0 < W; x0 += kCols) {
@@ -53,11 +75,8 @@ extern "C" long long ll_emulate(const uint8_t* cls, int H, int W, int slab_rows,
                     if (v == 1) weak[r * kWords + (c >> 5)] |= 1u << (c & 31);
                     if (v == 255) strong[r * kWords + (c >> 5)] |= 1u << (c & 31);
                 }
-            for (int r = 0; r < kRows; ++r)
-                for (int k = 0; k < kWords; ++k) init_word(weak.data(), strong.data(), lab.data(), r, k);
-            for (int r = 0; r < kRows; ++r)
-                for (int k = 0; k < kWords; ++k)
-                    link_word(weak.data(), lab.data(), r, k, /*skip_01_10=*/(row0 + y0 + r == 0) && x0 == 0, amin);
+            for_words([&](int r, int k) { init_word(weak.data(), strong.data(), lab.data(), r, k); });
+            for_words([&](int r, int k) { link_word(weak.data(), lab.data(), r, k, /*skip_01_10=*/(row0 + y0 + r == 0) && x0 == 0, amin); });
             const int gbase = y0 * W + x0;
             for (int r = 0; r < kRows; ++r)
                 for (int k = 0; k < kWords; ++k) {

@@ -18,19 +18,21 @@ def emul(tmp_path_factory):
     if shutil.which("g++") is None:
         pytest.skip("g++ not available")
     so = tmp_path_factory.mktemp("ll") / "libll_emul.so"
-    subprocess.run(["g++", "-std=c++14", "-O2", "-fPIC", "-shared", "-x", "c++", f"-I{ROOT / 'canny_edge_b200' / 'csrc'}",
+    subprocess.run(["g++", "-std=c++14", "-O2", "-pthread", "-fPIC", "-shared", "-x", "c++", f"-I{ROOT / 'canny_edge_b200' / 'csrc'}",
                     str(ROOT / "tests" / "cpp" / "local_link_emul.cpp"), "-o", str(so)], check=True, capture_output=True, text=True)
     lib = C.CDLL(str(so))
     lib.ll_emulate.restype = C.c_longlong
     lib.ll_emulate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.ll_emulate_mt.restype = C.c_longlong
+    lib.ll_emulate_mt.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
     return lib
 
 
-def run(emul, oracle, cls, slab_rows=64):
+def run(emul, oracle, cls, slab_rows=64, threads=1):
     cls = np.ascontiguousarray(cls, np.uint8)
     h, w = cls.shape
     out = np.empty_like(cls)
-    visited = emul.ll_emulate(cls.ctypes.data, h, w, slab_rows, 0, out.ctypes.data)
+    visited = emul.ll_emulate_mt(cls.ctypes.data, h, w, slab_rows, 0, out.ctypes.data, threads)
     nms = np.where(cls == 255, HI, np.where(cls == 1, LO, 0)).astype(np.int16)
     want = oracle.hysteresis(nms, LO, HI)
     bad = np.argwhere(out.astype(np.int16) != want)
@@ -89,3 +91,13 @@ def test_only_border_pixels_reach_the_global_kernel(emul, oracle):
     cls = np.where(r < 0.002, 255, np.where(r < 0.05, 1, 0))
     visited, weak = run(emul, oracle, cls)
     assert visited < 0.08 * weak      # (2*124 + 2*62) / (64*124) = 4.7 % of the tile
+
+
+def test_concurrent_linking(emul, oracle):
+    """The same phases on 8 host threads with real atomics: dense maps with large components, repeated so that different
+    interleavings of the lock-free unions occur."""
+    rng = np.random.default_rng(21)
+    for rep in range(6):
+        r = rng.random((128, 248))
+        cls = np.where(r < 0.003, 255, np.where(r < 0.55, 1, 0))
+        run(emul, oracle, cls, threads=8)

@@ -16,7 +16,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libcanny_b200.so"
 SOURCES = ["front.cu", "front2.cu", "hysteresis.cu", "stages.cu", "synth.cu", "band.cu", "selftest.cu", "api.cu"]
-HEADERS = ["internal.h", "front_common.cuh", "canny_math.h", "ccl.cuh", "exact_math.cuh", "../../include/canny_b200.h"]
+HEADERS = sorted(p.name for p in CSRC.glob("*.h")) + sorted(p.name for p in CSRC.glob("*.cuh")) + ["../../include/canny_b200.h"]
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3",

@@ -304,14 +304,12 @@ static int check_image(const void* in, const void* out, int h, int w) {
     return B200_OK;
 }
 
-static void fill_thresholds(FrontParams& p, int lo, int hi) {
-    // class of a kept pixel with squared magnitude n: candidate iff mag >= lo  <=>  n >= lo^2 (lo > 0), always if lo <= 0
-    const long long kBig = 0x7fffffff;
-    auto sq = [&](int v) -> int { if (v <= 0) return 0; long long s = (long long)v * v; return (int)std::min(s, kBig); };
-    p.lo = lo; p.hi = hi;
-    p.lo2 = sq(lo);
-    p.hi2 = sq(hi);
-    p.cls_zero = (0 >= lo) ? ((0 >= hi) ? 255 : 1) : 0;  // what a suppressed pixel (value 0) is: src/utils.cpp:328-333
+static int check_thresholds(int lo, int hi) {
+    if (!thresholds_supported(lo, hi)) {
+        set_error("thresholds minVal=%d > 255 >= maxVal=%d: the reference's result depends on its flood order there (src/utils.cpp:327-340); not reproduced", lo, hi);
+        return B200_ERR_UNSUPPORTED;
+    }
+    return B200_OK;
 }
 
 // Runs front + hysteresis on device-resident frames [f0, f0+nf) using workspace slot `slot` on stream st.
@@ -333,12 +331,8 @@ static int run_frames_device(b200_ctx* ctx, cudaStream_t st, int slot, const uin
     // only a launch that failed half-way leaves it dirty
     if (ctx->list_dirty[slot]) CB_CUDA(cudaMemsetAsync(fp.kept_count, 0, 64, st));
     ctx->list_dirty[slot] = true;
-    // EXPERIMENTAL (B200_CANNY_LOCAL_LINK=1, not yet validated on hardware): tile-local hysteresis linking in the front kernel
-    static const bool want_local = [] { const char* e = getenv("B200_CANNY_LOCAL_LINK"); return e && e[0] == '1'; }();
-    if (want_local && ensure_ws(ctx->ws_border[slot], ctx->ws_list[slot].bytes) == B200_OK)
-        fp.border_list = reinterpret_cast<uint32_t*>(ctx->ws_border[slot].ptr);
-    bool sparse = false, local = false;
-    CB_TRY(launch_front(ctx, st, fp, &sparse, &local));
+    bool sparse = false;
+    CB_TRY(launch_front(ctx, st, fp, &sparse));
     static const long long dense_div = [] { const char* e = getenv("B200_CANNY_DENSE_DIV"); return e ? atoll(e) : 8LL; }();
     // weak-pixel count of the previous launch of this slot (written into mapped pinned memory by its kernels, never waited for)
     const unsigned int prev_kept = *reinterpret_cast<volatile unsigned int*>(&ctx->h_kept[slot]);
@@ -349,7 +343,6 @@ static int run_frames_device(b200_ctx* ctx, cudaStream_t st, int slot, const uin
     memset(&hp, 0, sizeof(hp));
     hp.cls = d_out;
     hp.list = (sparse && !dense) ? fp.kept_list : nullptr;
-    if (hp.list && local) hp.border_list = fp.border_list;
     hp.ctr = sparse ? fp.kept_count : nullptr;
     hp.h_kept = ctx->d_kept + slot;
     hp.kept_prev = prev_kept;
@@ -364,8 +357,10 @@ static int run_frames_device(b200_ctx* ctx, cudaStream_t st, int slot, const uin
 // bytes of the weak-pixel list for nf frames of h x w: a counter block + one 32-bit entry per pixel (worst case: all weak)
 static size_t list_bytes(int nf, int h, int w) { return 64 + (size_t)nf * (size_t)h * (size_t)w * 4; }
 
+constexpr int kMaxChunkFrames = 65535;
 static int auto_chunk_frames(const b200_ctx* ctx, int h, int w, int n_frames) {
-    if (ctx->chunk_frames > 0) return std::min(ctx->chunk_frames, n_frames);
+    // a chunk's frame count is gridDim.z of the front kernel (gridDim.y of the tile merge / final kernels): at most 65535
+    if (ctx->chunk_frames > 0) return std::min(std::min(ctx->chunk_frames, n_frames), kMaxChunkFrames);
     const long long px = (long long)h * w;
     // ~75 Mpix per chunk (9 frames of 4K): measured best on the 512-frame batch (213 Gpix/s against 189 at 4 frames and 204 at
     // 16): long enough launches that the front kernel's last partly-filled wave matters little, short enough that the two
@@ -373,7 +368,7 @@ static int auto_chunk_frames(const b200_ctx* ctx, int h, int w, int n_frames) {
     // a chunk (75 MB) still fits the 126 MB L2 when hysteresis reads it
     long long f = (75LL << 20) / px;
     if (f < 1) f = 1;
-    return (int)std::min<long long>(f, n_frames);
+    return (int)std::min<long long>(std::min<long long>(f, n_frames), kMaxChunkFrames);
 }
 
 }  // namespace cb
@@ -435,7 +430,7 @@ int b200_ctx_destroy(b200_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     auto rel = [](Workspace& w, bool pinned) { if (w.ptr) { if (pinned) cudaFreeHost(w.ptr); else cudaFree(w.ptr); w.ptr = nullptr; w.bytes = 0; } };
-    for (int i = 0; i < 3; ++i) { rel(c->ws_parent[i], false); rel(c->ws_list[i], false); rel(c->ws_border[i], false); rel(c->dev_in[i], false); rel(c->dev_out[i], false); }
+    for (int i = 0; i < 3; ++i) { rel(c->ws_parent[i], false); rel(c->ws_list[i], false); rel(c->dev_in[i], false); rel(c->dev_out[i], false); }
     rel(c->ws_planes, false); rel(c->ws_misc, false); rel(c->ws_band_parent, false); rel(c->ws_band_list, false); rel(c->ws_band_aux, false);
     if (c->gauss.d_w) cudaFree(c->gauss.d_w);
     if (c->h_kept) cudaFreeHost(c->h_kept);
@@ -587,6 +582,7 @@ int b200_nonmaximal(b200_ctx* ctx, const int16_t* magnitude, const int16_t* angl
 
 int b200_hysteresis(b200_ctx* ctx, int16_t* nms_inout, int h, int w, int lo, int hi) {
     CB_TRY(check_image(nms_inout, nms_inout, h, w));
+    CB_TRY(check_thresholds(lo, hi));
     CB_TRY(resolve_ctx(ctx));
     const long long px = (long long)h * w;
     Planes pl;
@@ -594,7 +590,7 @@ int b200_hysteresis(b200_ctx* ctx, int16_t* nms_inout, int h, int w, int lo, int
     CB_TRY(ensure_ws(ctx->ws_parent[0], (size_t)px * 4));
     cudaStream_t st = ctx->stream;
     CB_CUDA(cudaMemcpyAsync(pl.p16[0], nms_inout, (size_t)px * 2, cudaMemcpyHostToDevice, st));
-    CB_TRY(launch_classify_i16(ctx, st, pl.p16[0], pl.cls, (size_t)px, lo, hi));
+    CB_TRY(launch_classify_i16(ctx, st, pl.p16[0], pl.cls, (size_t)px, lo, effective_hi(hi)));
     HystParams hp;
     memset(&hp, 0, sizeof(hp));
     hp.cls = pl.cls; hp.parent = reinterpret_cast<int32_t*>(ctx->ws_parent[0].ptr);
@@ -609,6 +605,7 @@ int b200_hysteresis(b200_ctx* ctx, int16_t* nms_inout, int h, int w, int lo, int
 int b200_canny_steps(b200_ctx* ctx, const uint8_t* img, float sigma, int lo, int hi, int h, int w, int16_t* blur,
                      int16_t* magnitude, int16_t* angle, int16_t* nms, int16_t* edges) {
     CB_TRY(check_image(img, edges, h, w));
+    CB_TRY(check_thresholds(lo, hi));
     CB_TRY(resolve_ctx(ctx));
     CB_TRY(prepare_gauss(ctx, sigma));
     const long long px = (long long)h * w;
@@ -639,6 +636,7 @@ int b200_canny(b200_ctx* ctx, const uint8_t* img, float sigma, int lo, int hi, i
     // the map crosses PCIe bit-packed (1/16 of the int16 plane) and is expanded to the reference's 0 / 255 int16 values by the pool
     if ((long long)h * w >= kStageMinBytes && !packed_transfer_off() && img && edges && (is_pageable(img) || is_pageable(edges))) {
         CB_TRY(check_image(img, edges, h, w));
+        CB_TRY(check_thresholds(lo, hi));
         CB_TRY(resolve_ctx(ctx));
         CB_TRY(prepare_gauss(ctx, sigma));
         return batch_host_impl(ctx, img, 1, h, w, lo, hi, nullptr, edges, true);
@@ -654,6 +652,7 @@ int b200_bgr_to_gray_device(b200_ctx* ctx, const uint8_t* d_bgr, size_t n_px, ui
 
 int b200_canny_bgr(b200_ctx* ctx, const uint8_t* bgr, float sigma, int lo, int hi, int h, int w, uint8_t* gray_out, int16_t* edges) {
     CB_TRY(check_image(bgr, edges, h, w));
+    CB_TRY(check_thresholds(lo, hi));
     CB_TRY(resolve_ctx(ctx));
     CB_TRY(prepare_gauss(ctx, sigma));
     const long long px = (long long)h * w;
@@ -707,6 +706,7 @@ int b200_canny_bgr(b200_ctx* ctx, const uint8_t* bgr, float sigma, int lo, int h
 int b200_canny_batch_device(b200_ctx* ctx, const uint8_t* d_frames, int n_frames, int h, int w, float sigma, int lo,
                             int hi, uint8_t* d_edges) {
     CB_TRY(check_image(d_frames, d_edges, h, w));
+    CB_TRY(check_thresholds(lo, hi));
     if (n_frames <= 0) { set_error("n_frames must be positive"); return B200_ERR_INVALID_ARG; }
     CB_TRY(resolve_ctx(ctx));
     CB_TRY(prepare_gauss(ctx, sigma));
@@ -750,7 +750,7 @@ static int batch_host_impl(b200_ctx* ctx, const uint8_t* frames, int n_frames, i
     const long long px = (long long)h * w;
     // chunks of ~64 MB: big enough for full PCIe rate, small enough that three are in flight
     int chunk = ctx->chunk_frames > 0 ? ctx->chunk_frames : (int)std::max<long long>(1, (64LL << 20) / px);
-    chunk = std::min(chunk, n_frames);
+    chunk = std::min(std::min(chunk, n_frames), kMaxChunkFrames);
     const int n_chunks = (n_frames + chunk - 1) / chunk;
     const int n_slots = std::min(3, n_chunks);
     const bool stage_in = is_pageable(frames) && (long long)n_frames * px >= kStageMinBytes;
@@ -828,6 +828,7 @@ static bool packed_transfer_off() {
 int b200_canny_batch_host(b200_ctx* ctx, const uint8_t* frames, int n_frames, int h, int w, float sigma, int lo, int hi,
                           uint8_t* edges) {
     CB_TRY(check_image(frames, edges, h, w));
+    CB_TRY(check_thresholds(lo, hi));
     if (n_frames <= 0) { set_error("n_frames must be positive"); return B200_ERR_INVALID_ARG; }
     CB_TRY(resolve_ctx(ctx));
     CB_TRY(prepare_gauss(ctx, sigma));
@@ -858,6 +859,7 @@ int b200_unpack_edges_host(const uint8_t* bits, size_t n_px, void* out, int elem
 int b200_profile_stages_device(b200_ctx* ctx, const uint8_t* d_frames, int n_frames, int h, int w, float sigma, int lo, int hi,
                                uint8_t* d_edges, float* ms_out, int* launches_out) {
     CB_TRY(check_image(d_frames, d_edges, h, w));
+    CB_TRY(check_thresholds(lo, hi));
     if (!ms_out || !launches_out || n_frames <= 0) { set_error("bad argument"); return B200_ERR_INVALID_ARG; }
     CB_TRY(resolve_ctx(ctx));
     CB_TRY(prepare_gauss(ctx, sigma));

@@ -137,6 +137,7 @@ int b200_band_front(b200_ctx* ctx, const uint8_t* d_rows, int halo_above, int ha
     }
     if ((long long)band_rows * width >= (1LL << 31)) { set_error("band exceeds int indexing"); return B200_ERR_UNSUPPORTED; }
     if (!ctx) { set_error("band calls need an explicit context (they keep per-band state)"); return B200_ERR_INVALID_ARG; }
+    if (!thresholds_supported(lo, hi)) { set_error("thresholds minVal=%d > 255 >= maxVal=%d are not reproduced (src/utils.cpp:327-340)", lo, hi); return B200_ERR_UNSUPPORTED; }
     CB_CUDA(cudaSetDevice(ctx->device));
     CB_TRY(prepare_gauss(ctx, sigma));
     const int need = ctx->gauss.radius + 2;
@@ -161,12 +162,7 @@ int b200_band_front(b200_ctx* ctx, const uint8_t* d_rows, int halo_above, int ha
     fp.out_row0 = row0; fp.out_rows = band_rows; fp.n_frames = 1;
     fp.cls = d_edges; fp.out_frame_stride = px;
     fp.w = ctx->gauss.d_w; fp.count = ctx->gauss.d_count; fp.radius = ctx->gauss.radius;
-    {
-        const long long kBig = 0x7fffffff;
-        auto sq = [&](int v) -> int { if (v <= 0) return 0; long long s = (long long)v * v; return (int)(s < kBig ? s : kBig); };
-        fp.lo = lo; fp.hi = hi; fp.lo2 = sq(lo); fp.hi2 = sq(hi);
-        fp.cls_zero = (0 >= lo) ? ((0 >= hi) ? 255 : 1) : 0;
-    }
+    fill_thresholds(fp, lo, hi);
     fp.parent = reinterpret_cast<int32_t*>(ctx->ws_band_parent.ptr);
     fp.kept_count = reinterpret_cast<unsigned int*>(ctx->ws_band_list.ptr);
     fp.kept_list = reinterpret_cast<uint32_t*>(ctx->ws_band_list.ptr) + 16;

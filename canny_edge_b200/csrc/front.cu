@@ -549,10 +549,9 @@ static int launch_front_v1(b200_ctx* ctx, cudaStream_t st, const FrontParams& p_
 
 // Dispatcher: the lean kernel (front2.cu) for the hot configuration — compile-time radius, no spill planes,
 // ordinary sigma; front_kernel above for everything else.  B200_CANNY_FRONT=1 forces the first kernel (A/B runs).
-int launch_front(b200_ctx* ctx, cudaStream_t st, const FrontParams& p_in, bool* sparse_out, bool* local_out) {
+int launch_front(b200_ctx* ctx, cudaStream_t st, const FrontParams& p_in, bool* sparse_out) {
     FrontParams p = p_in;
     if (sparse_out) *sparse_out = false;
-    if (local_out) *local_out = false;
     p.ieee_div = ctx->gauss.tiny ? 1 : 0;
     const int radius = p.radius;
     if (radius < 1 || radius > B200_MAX_RADIUS) {
@@ -566,9 +565,9 @@ int launch_front(b200_ctx* ctx, cudaStream_t st, const FrontParams& p_in, bool* 
         // whole-plane labelling has to run
         const bool sparse = p.parent != nullptr && p.kept_list != nullptr && p.kept_count != nullptr && p.cls_zero == 0 &&
                             (long long)p.n_frames * p.out_frame_stride < (1LL << 31);
-        if (!sparse) { p.parent = nullptr; p.kept_list = nullptr; p.kept_count = nullptr; p.border_list = nullptr; }
+        if (!sparse) { p.parent = nullptr; p.kept_list = nullptr; p.kept_count = nullptr; }
         if (sparse_out) *sparse_out = sparse;
-        return launch_front2(ctx, st, p, local_out);
+        return launch_front2(ctx, st, p);
     }
     return launch_front_v1(ctx, st, p);
 }

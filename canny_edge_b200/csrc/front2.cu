@@ -25,7 +25,6 @@
 #include "exact_math.cuh"
 #include "front_common.cuh"
 #include "internal.h"
-#include "local_link.cuh"
 
 namespace cb {
 namespace f2 {
@@ -54,13 +53,13 @@ __host__ __device__ constexpr int temp_rows_for(int radius, int slab) {
 }
 
 struct SmemLayout {
-    int in_off, temp_off, vu_off, ent_off, bits_off, sbits_off, tab_off, w_off, bar_off, total;
+    int in_off, temp_off, vu_off, ent_off, bits_off, tab_off, w_off, bar_off, total;
 };
 // staged input slabs: two (the next slab's TMA is in flight while this one is blurred) unless the wide temp buffer of a large
 // radius would then push a CTA past half an SM's shared memory — with one buffer the next slab is requested as soon as the row
 // pass has read this one and lands during the column pass and phase 3
 __host__ __device__ constexpr int in_bufs_for(int radius) { return radius > 9 ? 1 : 2; }
-__host__ __device__ constexpr SmemLayout smem_layout(int radius, int slab, bool local_link = false) {
+__host__ __device__ constexpr SmemLayout smem_layout(int radius, int slab) {
     SmemLayout L{};
     int o = 0;
     L.in_off = o;   o += in_bufs_for(radius) * slab * in_pitch_for(radius);
@@ -69,7 +68,6 @@ __host__ __device__ constexpr SmemLayout smem_layout(int radius, int slab, bool 
     L.vu_off = o;   o += (slab + 2) * kVuPitch * 4;
     L.ent_off = o;  o += slab * 64 * 2;                        // candidate lists: at most one 16-bit entry per (class row, lane, pixel pair)
     L.bits_off = o; o += slab * 4 * 4;                         // weak-pixel bitmap of the slab's class rows: 4 words per row
-    L.sbits_off = o; o += local_link ? slab * 4 * 4 : 0;       // strong-pixel bitmap (tile-local linking only)
     L.tab_off = o;  o += 2 * (radius + 1) * (radius + 1) * 4;  // count table, reciprocal table
     L.w_off = o;    o += (2 * radius + 1) * 4;
     o = (o + 15) & ~15;
@@ -101,9 +99,7 @@ constexpr int kBias4 = (int)(4u * 0x4B000000u);  // 4 * bias mod 2^32 = 0x2C0000
 // register file free, so blocks of the small latency-bound hysteresis kernels of the PREVIOUS chunk (other stream) become
 // resident next to them instead of waiting for a front CTA to retire: the front kernel alone gets 1.7 % slower, the chunk
 // pipeline 2.3 % faster on the bench frames and 8 % faster on photographic content (112 / 104 / 88 / 80 measured too: 96 wins).
-// LL: tile-local hysteresis linking (local_link.cuh; experimental, see launch_front2) instead of handing every weak pixel to the
-// global link kernel.
-template <int R, bool USE_TMA, int DIV, int SLAB, bool LL = false>
+template <int R, bool USE_TMA, int DIV, int SLAB>
 __global__ void __maxnreg__(SLAB == 64 ? 96 : 64)
 front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -115,8 +111,7 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
     constexpr int kEntPerWarp = (SLAB / 8) * 64;
     static_assert(SLAB == 32 || SLAB == 64, "row/column pass mappings are written for 32- and 64-row slabs");
     static_assert(2 * R + 2 <= SLAB, "the saved tail must not overlap the rows it is copied from");
-    constexpr SmemLayout L = smem_layout(R, SLAB, LL);
-    static_assert(!LL || SLAB == 64, "tile-local linking is written for 64-row slabs (one thread per bitmap word)");
+    constexpr SmemLayout L = smem_layout(R, SLAB);
     constexpr int in_pitch = in_pitch_for(R);
     constexpr int T0 = 2 * R + 2;  // temp buffer row of the first row of the current slab
 
@@ -129,10 +124,6 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
     const uint32_t bar0 = smem_u32(smem + L.bar_off);
     uint16_t* s_ent = reinterpret_cast<uint16_t*>(smem + L.ent_off);
     uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem + L.bits_off);
-    uint32_t* s_sbits = reinterpret_cast<uint32_t*>(smem + L.sbits_off);     // LL only
-    // LL: tile-local labels, 64 x 124 int32, in VU rows 2..62: free from barrier (C) until the next slab's column pass
-    int* s_lab = reinterpret_cast<int*>(smem + L.vu_off) + 2 * kVuPitch;
-    static_assert(!LL || (ll::kRows * ll::kPitch <= (SLAB - 2) * kVuPitch), "label array must stay clear of VU rows 64, 65");
     const bool sparse = p.kept_list != nullptr;                  // uniform: also fill parent[] and the weak-pixel list
     int32_t* s_np = reinterpret_cast<int32_t*>(s_temp + T0 * kTempPitch);   // n-plane: the temp rows phase 1 refills next slab
 
@@ -158,7 +149,6 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
     }
     for (int i = tid; i < 2 * R + 1; i += kThreads) s_w[i] = p.w[i];
     if (tid < 4 * kSlab) s_bits[tid] = 0;
-    if (LL && tid < 4 * kSlab) s_sbits[tid] = 0;
     if (USE_TMA && tid == 0) {
         mbar_init(bar0, 1);
         mbar_init(bar0 + 8, 1);
@@ -211,10 +201,6 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
     uint32_t pend_bits = 0;
     unsigned int pend_base = 0;
     int pend_off = 0, pend_g0 = 0;
-    // LL: the same for the border list (the weak pixels the global link kernel still visits)
-    uint32_t pend_bbits = 0;
-    unsigned int pend_bbase = 0;
-    int pend_boff = 0;
     auto flush_pending = [&]() {
         const unsigned int base = __shfl_sync(0xffffffffu, pend_base, 0);
         uint32_t* dst = p.kept_list + base + pend_off;
@@ -225,17 +211,6 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
             *dst++ = (uint32_t)(pend_g0 + b);
         }
         pend_bits = 0;
-        if (LL) {
-            const unsigned int bbase = __shfl_sync(0xffffffffu, pend_bbase, 0);
-            uint32_t* bdst = p.border_list + bbase + pend_boff;
-            uint32_t bm = pend_bbits;
-            while (bm) {
-                const int b = __ffs(bm) - 1;
-                bm &= bm - 1;
-                *bdst++ = (uint32_t)(pend_g0 + b);
-            }
-            pend_bbits = 0;
-        }
     };
 
     for (int k = 0; k < n_slabs; ++k) {
@@ -539,12 +514,7 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
                         if (na[e] < m2 && nb[e] < m2) {
                             const bool strong = n >= p.hi2;
                             orow[e] = strong ? (uint8_t)255 : (uint8_t)1;
-                            if (LL) {
-                                // tile-local linking: weak AND strong pixels go into the slab's bitmaps; the union-find slots
-                                // are written after the local linking (phase 4)
-                                const int col = c0 + e - 1;                   // class column within the strip: j - 2
-                                atomicOr(&(strong ? s_sbits : s_bits)[rr * 4 + (col >> 5)], 1u << (col & 31));
-                            } else if (sparse && !strong) {
+                            if (sparse && !strong) {
                                 // hand-over to the list-driven hysteresis kernels: only WEAK pixels need any work there (a strong
                                 // pixel is final; its neighbours find it through the class map).  The weak pixel gets its union-
                                 // find slot (itself) and a bit in the slab's bitmap, from which the list entries are made once
@@ -560,52 +530,7 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
             }
         }
         __syncthreads();  // (C) VU, n-plane and list reads done; the slab's weak-pixel bitmap is complete
-        if (LL) {
-            // ===================== phase 4 (LL): hysteresis linking inside the tile (local_link.cuh) =====================
-            // thread = one bitmap word: class row rr = tid >> 2, columns 32*(tid & 3) .. of the strip
-            const int r4 = tid >> 2, k4 = tid & 3;
-            ll::init_word(s_bits, s_sbits, s_lab, r4, k4);
-            __syncthreads();  // (L1) every weak pixel of the tile has a label
-            ll::link_word(s_bits, s_lab, r4, k4, /*skip_01_10=*/(y_base + r4 == 0) && x0 == 0,
-                          [](int* addr, int v) { return atomicMin(addr, v); });
-            __syncthreads();  // (L2) the tile's forest is final
-            const uint32_t wbits = s_bits[tid];
-            // launch-relative index of (class row 0, class column 0) of this tile
-            const int gbase = (int)((long long)frame * p.out_frame_stride + (long long)(y_base - p.out_row0) * W + x0);
-            {
-                uint32_t m = wbits;
-                while (m) {
-                    const int c = 32 * k4 + (__ffs(m) - 1);
-                    m &= m - 1;
-                    p.parent[gbase + r4 * W + c] = ll::global_parent(static_cast<const volatile int*>(s_lab), r4 * ll::kPitch + c, gbase, W);
-                }
-            }
-            pend_bits = wbits;
-            pend_bbits = ll::border_bits(wbits, r4, k4, cq_lo - 1, cq_hi - 1, min(kTW - 1, W - 1 - x0));
-            s_bits[tid] = 0;      // nobody reads another thread's words after (L2)
-            s_sbits[tid] = 0;
-            // reserve room in both lists with ONE 64-bit atomicAdd per warp: {all weak pixels, border pixels} live in ctr[0], ctr[1]
-            const int cnt = __popc(pend_bits) | (__popc(pend_bbits) << 16);    // <= 1024 per warp each: the halves cannot carry
-            int incl = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += t;
-            }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
-            pend_base = 0;
-            pend_bbase = 0;
-            if (total && lane == 0) {
-                const unsigned long long add = (unsigned long long)(total & 0xffff) | ((unsigned long long)(total >> 16) << 32);
-                const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(p.kept_count), add);
-                pend_base = (unsigned int)old;
-                pend_bbase = (unsigned int)(old >> 32);
-            }
-            const int excl = incl - cnt;
-            pend_off = excl & 0xffff;
-            pend_boff = excl >> 16;
-            pend_g0 = gbase + r4 * W + 32 * k4;
-        } else if (sparse) {
+        if (sparse) {
             // append this slab's weak pixels to the launch-wide list: every warp counts the bits of its 32 bitmap words and reserves
             // room with ONE global atomicAdd.  The atomic's round trip is hidden behind the next slab's row pass: the entries are
             // written by flush_pending() after it (and once more after the last slab).
@@ -637,18 +562,18 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int R, bool USE_TMA, int DIV, int SLAB, bool LL = false>
+template <int R, bool USE_TMA, int DIV, int SLAB>
 static int launch_one2(b200_ctx* ctx, cudaStream_t st, const FrontParams& p, const CUtensorMap& tmap, dim3 grid) {
-    const f2::SmemLayout L = f2::smem_layout(R, SLAB, LL);
+    const f2::SmemLayout L = f2::smem_layout(R, SLAB);
     static bool configured[64] = {false};  // per instantiation, per device
     if (!configured[ctx->device & 63]) {
-        CB_CUDA(cudaFuncSetAttribute(f2::front2_kernel<R, USE_TMA, DIV, SLAB, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-        CB_CUDA(cudaFuncSetAttribute(f2::front2_kernel<R, USE_TMA, DIV, SLAB, LL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CB_CUDA(cudaFuncSetAttribute(f2::front2_kernel<R, USE_TMA, DIV, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        CB_CUDA(cudaFuncSetAttribute(f2::front2_kernel<R, USE_TMA, DIV, SLAB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured[ctx->device & 63] = true;
     }
     {
         ProfScope ps(ctx, st, 0);
-        f2::front2_kernel<R, USE_TMA, DIV, SLAB, LL><<<grid, f2::kThreads, L.total, st>>>(p, tmap);
+        f2::front2_kernel<R, USE_TMA, DIV, SLAB><<<grid, f2::kThreads, L.total, st>>>(p, tmap);
     }
     CB_CUDA(cudaGetLastError());
     ctx->launches++;
@@ -693,9 +618,8 @@ static int choose_bands2(const b200_ctx* ctx, int out_rows, int strips, int fram
     return best;
 }
 
-int launch_front2(b200_ctx* ctx, cudaStream_t st, const FrontParams& p_in, bool* local_out) {
+int launch_front2(b200_ctx* ctx, cudaStream_t st, const FrontParams& p_in) {
     FrontParams p = p_in;
-    if (local_out) *local_out = false;
     const int radius = p.radius;
     const int strips = (p.width + f2::kTW - 1) / f2::kTW;
     p.tiles_x = strips;
@@ -710,17 +634,6 @@ int launch_front2(b200_ctx* ctx, cudaStream_t st, const FrontParams& p_in, bool*
     CB_TRY(make_input_tensor_map(p, f2::in_pitch_for(radius), slab, &tmap, &use_tma));
     const int div3 = ctx->gauss.div_mode;
     p.div_c = ctx->gauss.div_c;
-    // EXPERIMENTAL tile-local hysteresis linking (local_link.cuh): requested by the caller through p.border_list, built for the
-    // headline configuration only (TMA staging, sigma 1.4's radius 5); anything else runs the regular kernel, and the caller
-    // learns which through local_out
-    if (p.border_list && p.kept_list && use_tma && radius == 5) {
-        if (local_out) *local_out = true;
-        if (div3 == 1) return launch_one2<5, true, 1, 64, true>(ctx, st, p, tmap, grid);
-        if (div3 == 3) return launch_one2<5, true, 3, 64, true>(ctx, st, p, tmap, grid);
-        return launch_one2<5, true, 5, 64, true>(ctx, st, p, tmap, grid);
-    }
-    p.border_list = nullptr;
-
     switch (radius) {
         case 2: return launch_r2<2, 64>(ctx, st, p, tmap, grid, use_tma, div3);
         case 3: return launch_r2<3, 64>(ctx, st, p, tmap, grid, use_tma, div3);

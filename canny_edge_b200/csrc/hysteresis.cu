@@ -263,14 +263,11 @@ ccl_final_kernel(const HystParams p) {
 // the two diagonals reach the pixel through S's own links) are united with it, so every weak-weak pair is visited exactly once,
 // from its earlier endpoint in raster order.  The pair (0,1)-(1,0) of the GLOBAL image is skipped in both directions (see the
 // file header): the one-way link is applied by the last block of this kernel, below.
-// BORDER (experimental tile-local linking, front2.cu LL): the front kernel has already linked every tile; only the weak pixels
-// on tile borders are walked (p.border_list, count ctr[1]; finished-block counter ctr[3]).
-template <bool BORDER>
 __global__ void __launch_bounds__(256)
 ccl_sparse_link_kernel(const HystParams p) {
     const unsigned int n_all = p.ctr[0];
-    const unsigned int n = BORDER ? p.ctr[1] : n_all;
-    const uint32_t* const walk = BORDER ? p.border_list : p.list;
+    const unsigned int n = n_all;
+    const uint32_t* const walk = p.list;
     const int W = p.width, Hh = p.rows;
     const unsigned int fs = (unsigned int)p.frame_stride;
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -307,7 +304,7 @@ ccl_sparse_link_kernel(const HystParams p) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        s_last = atomicAdd(p.ctr + (BORDER ? 3 : 1), 1u) == gridDim.x - 1;
+        s_last = atomicAdd(p.ctr + 1, 1u) == gridDim.x - 1;
     }
     __syncthreads();
     if (!s_last) return;
@@ -326,7 +323,6 @@ ccl_sparse_link_kernel(const HystParams p) {
         if (p.h_kept && ((n_all > p.kept_thresh) != (p.kept_prev > p.kept_thresh))) *p.h_kept = n_all;
         p.ctr[0] = 0;
         p.ctr[1] = 0;
-        if (BORDER) p.ctr[3] = 0;
     }
 }
 
@@ -356,8 +352,7 @@ int launch_ccl_label(b200_ctx* ctx, cudaStream_t st, const HystParams& p_in) {
     HystParams p = p_in;
     if (p.list) {
         ProfScope ps(ctx, st, 1);
-        if (p.border_list) ccl_sparse_link_kernel<true><<<sparse_grid(ctx), 256, 0, st>>>(p);
-        else ccl_sparse_link_kernel<false><<<sparse_grid(ctx), 256, 0, st>>>(p);
+        ccl_sparse_link_kernel<<<sparse_grid(ctx), 256, 0, st>>>(p);
         CB_CUDA(cudaGetLastError());
         ctx->launches++;
         return B200_OK;

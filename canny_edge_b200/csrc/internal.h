@@ -78,10 +78,29 @@ struct FrontParams {
                             // frame*out_frame_stride + pixel (strong pixels need no slot: they are final)
     uint32_t* kept_list;    // launch-relative indices of all weak pixels, in no particular order
     unsigned int* kept_count;  // number of entries: word 0 of the list's counter block (see HystParams::ctr); zero at launch
-    uint32_t* border_list;     // EXPERIMENTAL tile-local linking (front2.cu LL, local_link.cuh): when set, front2 links the weak
-                               // pixels of every tile itself, writes final tile-local roots into parent[] and lists here the weak
-                               // pixels on tile borders, the only ones the global link kernel still has to visit (count: ctr[1])
 };
+
+// ---- thresholds ---------------------------------------------------------------------------------
+// The reference accepts any int pair (only its CLI checks 0 <= minVal < maxVal <= 255, src/main.cpp:63-76).  What
+// src/utils.cpp:322-342 then does:
+//   * maxVal > 255: every flooded pixel is written as EDGE = 255 (src/utils.cpp:368) and the second scan zeroes everything below
+//     maxVal (:336-340) -> the map is ALL ZERO.  Reproduced: no pixel is ever strong (hi2 = INT_MAX), so every weak pixel
+//     resolves to 0.
+//   * minVal > 255 >= maxVal: the first scan re-zeroes flooded pixels it has not passed yet (255 < minVal, :328-329), so the
+//     result depends on the raster order of the flood starts.  Not reproduced: B200_ERR_UNSUPPORTED.
+//   * everything else (including minVal >= maxVal and negative values) follows from the two comparisons and is reproduced.
+inline bool thresholds_supported(int lo, int hi) { return !(lo > 255 && hi <= 255); }
+// maxVal as the classification kernels must see it: above every representable magnitude when the reference's map is all zero
+inline int effective_hi(int hi) { return hi > 255 ? 0x7fffffff : hi; }
+inline void fill_thresholds(FrontParams& p, int lo, int hi) {
+    // class of a kept pixel with squared magnitude n: candidate iff mag >= lo  <=>  n >= lo^2 (lo > 0), always if lo <= 0
+    const long long kBig = 0x7fffffff;
+    auto sq = [&](int v) -> int { if (v <= 0) return 0; long long s = (long long)v * v; return (int)(s < kBig ? s : kBig); };
+    p.lo = lo; p.hi = hi;
+    p.lo2 = sq(lo);
+    p.hi2 = hi > 255 ? (int)kBig : sq(hi);   // magnitudes stay below 1443, n below 2^22: INT_MAX is never reached
+    p.cls_zero = (0 >= lo) ? ((0 >= hi) ? 255 : 1) : 0;  // what a suppressed pixel (value 0) is: src/utils.cpp:328-333
+}
 
 // ---- parameters of the hysteresis (connected components) kernels ---------------------------------
 struct HystParams {
@@ -100,14 +119,11 @@ struct HystParams {
     //   ctr[0]  live entry count (front2's atomicAdd)        ctr[1]  link-kernel blocks that have finished
     //   ctr[2]  entry count of the finished launch: written, with h_kept, by the last block of the link kernel (or by
     //           list_retire_kernel on the tile-based path), which also zeroes ctr[0] and ctr[1] for the next launch
-    // (experimental tile-local linking: ctr[1] is the border list's live count instead and ctr[3] counts the finished blocks)
     unsigned int* ctr;
     unsigned int* h_kept;        // mapped pinned host word that receives the entry count (density of the next launch's choice) ...
     unsigned int kept_prev, kept_thresh;   // ... but only when it moves across the threshold: the host's last view of it and the
                                            // "tile-based labelling above this many weak pixels" bound (a write to host memory at the
                                            // end of every launch measured 1 % of the batch throughput)
-    const uint32_t* border_list; // experimental tile-local linking (front2.cu LL): when set, the link kernel walks only these weak
-                                 // pixels (count ctr[1]); `list` (count ctr[0]) is still what the resolve kernel walks
 };
 
 struct HostPool;  // api.cu
@@ -140,7 +156,6 @@ struct b200_ctx {
     cb::GaussTables gauss;
     cb::Workspace ws_parent[3];   // int32 union-find slots for one chunk, per pipeline slot
     cb::Workspace ws_list[3];     // kept-pixel lists for one chunk ([0..15] = counter block, entries from word 16), per pipeline slot
-    cb::Workspace ws_border[3];   // border-pixel lists (experimental tile-local linking), per pipeline slot
     cb::Workspace ws_band_list;   // kept-pixel list of the resident band
     cb::Workspace ws_planes;      // stage-API scratch planes
     cb::Workspace ws_misc;
@@ -193,12 +208,12 @@ int host_window(float sigma);
 
 // front.cu
 // *sparse_out (optional) tells whether the kernel that ran filled p.parent / p.kept_list
-// sparse_out: the kernel produced the weak-pixel list; local_out: it also linked every tile itself and produced the border list
-int launch_front(b200_ctx* ctx, cudaStream_t st, const FrontParams& p, bool* sparse_out = nullptr, bool* local_out = nullptr);
+// sparse_out: the kernel produced the weak-pixel list
+int launch_front(b200_ctx* ctx, cudaStream_t st, const FrontParams& p, bool* sparse_out = nullptr);
 int make_input_tensor_map(const FrontParams& p, int box_cols, int box_rows, CUtensorMap_st* tmap, bool* use_tma);
 // front2.cu
 bool front2_supports(int radius);
-int launch_front2(b200_ctx* ctx, cudaStream_t st, const FrontParams& p, bool* local_out = nullptr);
+int launch_front2(b200_ctx* ctx, cudaStream_t st, const FrontParams& p);
 // selftest.cu
 int check_div_mode_device(b200_ctx* ctx, float b, float y, float* c, int* mode);
 // hysteresis.cu

@@ -258,6 +258,7 @@ def canny_bands_virtual(img: np.ndarray, n_bands: int, sigma: float, min_val: in
             edges.append(e)
             recs.append(r)
         all_records = torch.cat(recs)
+        torch.cuda.synchronize(dev)   # torch.cat ran on torch's stream; the contexts finalise on their own streams
         for p, e in zip(pipes, edges):
             p.finalize(all_records, e)
             p.ctx.synchronize()

@@ -12,9 +12,12 @@
  * Error convention.  The reference returns void and checks no CUDA status (src/cuda.cu:83-101).  The
  * C ABI returns an int status (0 == B200_OK) and keeps a thread-local message readable through
  * b200_last_error().  Argument domains follow the reference: height,width >= 2 (below that the
- * reference's gradient reads out of bounds, src/utils.cpp:117,158), sigma > 0; thresholds are accepted
- * over the whole int range and behave as src/utils.cpp:322-342 does (the CLI's 0 <= lo < hi <= 255
- * check lives in src/main.cpp:63-76 and stays there).
+ * reference's gradient reads out of bounds, src/utils.cpp:117,158), sigma > 0.  Thresholds: the CLI's
+ * 0 <= lo < hi <= 255 check lives in src/main.cpp:63-76 and stays there; the library accepts any int pair
+ * and behaves as src/utils.cpp:322-342 does — lo >= hi and negative values included, and max_val > 255
+ * gives the reference's ALL-ZERO map (its flood writes EDGE = 255, its second scan then removes everything
+ * below max_val) — with ONE exception: min_val > 255 >= max_val, where the reference's result depends on
+ * the raster order of its flood starts (:327-340), returns B200_ERR_UNSUPPORTED.
  */
 #ifndef CANNY_B200_H
 #define CANNY_B200_H

@@ -45,22 +45,27 @@ inline void show_plane(const char* title, short* plane, int height, int width) {
 // src/cuda.h:4 — Gaussian blur with a kernel generated from sigma (window = 1 + 2*ceil(3*sigma)).
 inline void cuda_gaussian(unsigned char*& img_h, float sigma, int height, int width, short int*& result_h) {
     result_h = new short[(size_t)height * width];
-    canny_b200_detail::check(b200_gaussian(nullptr, img_h, sigma, height, width, result_h), "cuda_gaussian");
+    const int st = b200_gaussian(nullptr, img_h, sigma, height, width, result_h);
+    if (st != B200_OK) { delete[] result_h; result_h = nullptr; }   // no leak, no dangling output on failure
+    canny_b200_detail::check(st, "cuda_gaussian");
 }
 
 // src/cuda.h:6 — Sobel magnitude and quantised angle (0/45/90/135). The input is NOT freed (as in src/cuda.cu:220-246).
 inline void cuda_sobel(short int*& img_h, int height, int width, short int*& magnitude_h, short int*& angle_h) {
     magnitude_h = new short[(size_t)height * width];
     angle_h = new short[(size_t)height * width];
-    canny_b200_detail::check(b200_sobel(nullptr, img_h, height, width, magnitude_h, angle_h), "cuda_sobel");
+    const int st = b200_sobel(nullptr, img_h, height, width, magnitude_h, angle_h);
+    if (st != B200_OK) { delete[] magnitude_h; delete[] angle_h; magnitude_h = nullptr; angle_h = nullptr; }
+    canny_b200_detail::check(st, "cuda_sobel");
 }
 
 // src/cuda.h:8 — non-maximal suppression (the misspelling is the reference's symbol name).
 inline void cuda_nonmaixmal_suppression(short int*& magnitude_h, short int*& angle_h, int height, int width,
                                         short int*& result_h) {
     result_h = new short[(size_t)height * width];
-    canny_b200_detail::check(b200_nonmaximal(nullptr, magnitude_h, angle_h, height, width, result_h),
-                             "cuda_nonmaixmal_suppression");
+    const int st = b200_nonmaximal(nullptr, magnitude_h, angle_h, height, width, result_h);
+    if (st != B200_OK) { delete[] result_h; result_h = nullptr; }
+    canny_b200_detail::check(st, "cuda_nonmaixmal_suppression");
 }
 
 // GPU twin of hysteresis() (src/utils.h:18, src/utils.cpp:322-342): in place, 0 / 255 on return.

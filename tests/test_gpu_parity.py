@@ -175,6 +175,31 @@ def test_threshold_domain(gpu_ctx, oracle):
         assert_same(f"hyst lo={lo} hi={hi}", cb.cuda_hysteresis(nms, lo, hi, ctx=gpu_ctx), oracle.hysteresis(nms, lo, hi))
 
 
+def test_thresholds_above_255(gpu_ctx, oracle):
+    """max_val > 255: the reference's flood writes EDGE = 255 and its second scan removes everything below max_val, so the map is
+    all zero (src/utils.cpp:336-340, 368) although magnitudes reach ~1442; min_val > 255 >= max_val is rejected (header)."""
+    rng = np.random.default_rng(12)
+    img = (rng.integers(0, 2, (9, 12)) * 255).astype(np.uint8).repeat(8, 0).repeat(8, 1)   # hard 0/255 blocks: magnitudes >> 255
+    nms = oracle.canny(img, 1.0, 20, 60, steps=True)[3]
+    assert int(nms.max()) > 600
+    for lo, hi in [(100, 300), (20, 256), (0, 1500), (300, 400), (-4, 1000), (255, 256), (100, 255), (600, 700)]:
+        want = oracle.canny(img, 1.0, lo, hi)
+        if hi > 255:
+            assert not want.any()
+        assert_same(f"lo={lo} hi={hi}", cb.cuda_canny(img, 1.0, lo, hi, ctx=gpu_ctx), want)
+        assert_same(f"hyst lo={lo} hi={hi}", cb.cuda_hysteresis(nms, lo, hi, ctx=gpu_ctx), oracle.hysteresis(nms, lo, hi))
+        frames = np.stack([img, img[::-1].copy()])
+        out = cb.canny_batch_host(frames, 1.0, lo, hi, ctx=gpu_ctx)
+        for f in range(2):
+            assert_same(f"batch lo={lo} hi={hi}", out[f].astype(np.int16), oracle.canny(frames[f], 1.0, lo, hi))
+    for lo, hi in [(256, 255), (300, 100), (1000, -1)]:
+        with pytest.raises(cb.CannyB200Error) as ei:
+            cb.cuda_canny(img, 1.0, lo, hi, ctx=gpu_ctx)
+        assert ei.value.status == 4   # B200_ERR_UNSUPPORTED
+        with pytest.raises(cb.CannyB200Error):
+            cb.cuda_hysteresis(nms, lo, hi, ctx=gpu_ctx)
+
+
 def test_random_hysteresis_vs_oracle(gpu_ctx, oracle):
     rng = np.random.default_rng(3)
     for h, w, dens in [(6, 6, 0.5), (64, 64, 0.4), (65, 130, 0.3), (129, 200, 0.45), (300, 257, 0.35), (70, 70, 0.9), (64, 128, 1.0)]:

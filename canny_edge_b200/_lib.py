@@ -55,13 +55,30 @@ SIGNATURES = {
     "b200_canny_bgr": (C.c_int, [_ctx, _u8p, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, _i16p]),
     "b200_bgr_to_gray_device": (C.c_int, [_ctx, _u8p, C.c_size_t, _u8p]),
     "b200_canny_batch_host": (C.c_int, [_ctx, _u8p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _u8p]),
+    "b200_canny_batch_host_packed": (C.c_int, [_ctx, _u8p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p]),
     "b200_canny_batch_device": (C.c_int, [_ctx, _u8p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _u8p]),
     "b200_profile_stages_device": (C.c_int, [_ctx, _u8p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _u8p, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "b200_profile_pipeline_device": (C.c_int, [_ctx, _u8p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _u8p, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "b200_hash_edges_device": (C.c_int, [_ctx, _u8p, C.c_size_t, C.c_ulonglong, C.POINTER(C.c_ulonglong)]),
     "b200_band_halo_rows": (C.c_int, [C.c_float]),
     "b200_band_record_count": (C.c_int, [C.c_int]),
     "b200_band_front": (C.c_int, [_ctx, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _u8p]),
     "b200_band_boundary_export": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_void_p]),
     "b200_band_finalize": (C.c_int, [_ctx, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]),
+    "b200_bands_unique_id": (C.c_int, [C.c_void_p]),
+    "b200_bands_create": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "b200_bands_create_group": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "b200_bands_destroy": (C.c_int, [C.c_void_p]),
+    "b200_bands_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "b200_bands_input": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "b200_bands_run": (C.c_int, [C.c_void_p, _u8p]),
+    "b200_bands_run_group": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]),
+    "b200_bands_begin": (C.c_int, [C.c_void_p, _u8p]),
+    "b200_bands_front": (C.c_int, [C.c_void_p]),
+    "b200_bands_finish": (C.c_int, [C.c_void_p]),
+    "b200_bands_check": (C.c_int, [C.c_void_p]),
+    "b200_bands_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "b200_bands_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "b200_synth_host": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int]),
     "b200_synth_device": (C.c_int, [_ctx, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int]),
     "b200_synth_rows_host": (C.c_int, [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int]),

@@ -15,7 +15,7 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libcanny_b200.so"
-SOURCES = ["front.cu", "front2.cu", "hysteresis.cu", "stages.cu", "synth.cu", "band.cu", "selftest.cu", "api.cu"]
+SOURCES = ["front.cu", "front2.cu", "hysteresis.cu", "stages.cu", "synth.cu", "band.cu", "bands_mgpu.cu", "selftest.cu", "api.cu"]
 HEADERS = sorted(p.name for p in CSRC.glob("*.h")) + sorted(p.name for p in CSRC.glob("*.cuh")) + ["../../include/canny_b200.h"]
 
 NVCC_FLAGS = [
@@ -66,7 +66,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         if verbose and out:
             print(out)
         objs.append(str(obj))
-    cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *objs, "-lcudart"]
+    cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *objs, "-lcudart", "-ldl"]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + res.stdout)

@@ -368,7 +368,10 @@ static int auto_chunk_frames(const b200_ctx* ctx, int h, int w, int n_frames) {
     // a chunk (75 MB) still fits the 126 MB L2 when hysteresis reads it
     long long f = (75LL << 20) / px;
     if (f < 1) f = 1;
-    return (int)std::min<long long>(std::min<long long>(f, n_frames), kMaxChunkFrames);
+    f = std::min<long long>(std::min<long long>(f, n_frames), kMaxChunkFrames);
+    // equal chunks: 64 frames run as 8 x 8, not 7 x 9 + 1 (a one-frame launch fills a tenth of the machine)
+    const long long n_chunks = (n_frames + f - 1) / f;
+    return (int)((n_frames + n_chunks - 1) / n_chunks);
 }
 
 }  // namespace cb
@@ -628,7 +631,7 @@ int b200_canny_steps(b200_ctx* ctx, const uint8_t* img, float sigma, int lo, int
 }
 
 static int batch_host_impl(b200_ctx* ctx, const uint8_t* frames, int n_frames, int h, int w, int lo, int hi, uint8_t* edges8,
-                           int16_t* edges16, bool packed);
+                           int16_t* edges16, bool packed, uint32_t* bits_out = nullptr);
 static bool packed_transfer_off();
 
 int b200_canny(b200_ctx* ctx, const uint8_t* img, float sigma, int lo, int hi, int h, int w, int16_t* edges) {
@@ -745,9 +748,12 @@ int b200_canny_batch_device(b200_ctx* ctx, const uint8_t* d_frames, int n_frames
 // Host buffers in, host buffers out: frames -> 0 / 255 edge maps, as bytes (edges8) or as the reference's int16 (edges16).
 // Chunks of frames are pipelined over three stream slots (H2D | kernels | D2H + host expansion).  Pageable caller memory is staged
 // through pinned buffers by the host pool; the maps come back bit-packed unless the job is small AND the output buffer is pinned.
+// bits_out: the caller takes the maps PACKED (b200_canny_batch_host_packed): frame f's bits start at word f * ceil(px / 32); the
+// packed chunks are copied straight into the caller's buffer and no host pass runs.
 static int batch_host_impl(b200_ctx* ctx, const uint8_t* frames, int n_frames, int h, int w, int lo, int hi, uint8_t* edges8,
-                           int16_t* edges16, bool packed) {
+                           int16_t* edges16, bool packed, uint32_t* bits_out) {
     const long long px = (long long)h * w;
+    const size_t frame_words = ((size_t)px + 31) / 32;
     // chunks of ~64 MB: big enough for full PCIe rate, small enough that three are in flight
     int chunk = ctx->chunk_frames > 0 ? ctx->chunk_frames : (int)std::max<long long>(1, (64LL << 20) / px);
     chunk = std::min(std::min(chunk, n_frames), kMaxChunkFrames);
@@ -755,7 +761,7 @@ static int batch_host_impl(b200_ctx* ctx, const uint8_t* frames, int n_frames, i
     const int n_slots = std::min(3, n_chunks);
     const bool stage_in = is_pageable(frames) && (long long)n_frames * px >= kStageMinBytes;
     if (edges16 && !packed) { set_error("internal: int16 output needs the packed path"); return B200_ERR_INVALID_ARG; }
-    const size_t chunk_bits_bytes = (((size_t)px * (size_t)chunk + 31) / 32) * 4;
+    const size_t chunk_bits_bytes = bits_out ? (size_t)chunk * frame_words * 4 : (((size_t)px * (size_t)chunk + 31) / 32) * 4;
     for (int s = 0; s < n_slots; ++s) {
         CB_TRY(ensure_ws(ctx->ws_parent[s], (size_t)px * 4 * (size_t)chunk));
         CB_TRY(ensure_ws(ctx->ws_list[s], list_bytes(chunk, h, w)));
@@ -763,11 +769,11 @@ static int batch_host_impl(b200_ctx* ctx, const uint8_t* frames, int n_frames, i
         CB_TRY(ensure_ws(ctx->dev_out[s], (size_t)px * (size_t)chunk));
         if (packed) {
             CB_TRY(ensure_ws(ctx->dev_bits[s], chunk_bits_bytes));
-            CB_TRY(ensure_ws(ctx->host_bits[s], chunk_bits_bytes, /*pinned_host=*/true));
+            if (!bits_out) CB_TRY(ensure_ws(ctx->host_bits[s], chunk_bits_bytes, /*pinned_host=*/true));
         }
         if (stage_in) CB_TRY(ensure_ws(ctx->host_in[s], (size_t)px * (size_t)chunk, /*pinned_host=*/true));
     }
-    HostPool* pool = (packed || stage_in) ? get_pool(ctx) : nullptr;
+    HostPool* pool = ((packed && !bits_out) || stage_in) ? get_pool(ctx) : nullptr;
     CB_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
     for (int s = 0; s < n_slots; ++s) CB_CUDA(cudaStreamWaitEvent(ctx->side[s], ctx->ev_fork, 0));
     auto finish_chunk = [&](int c) -> int {  // host side of chunk c: wait for its packed map, expand it into the caller's buffer
@@ -798,7 +804,16 @@ static int batch_host_impl(b200_ctx* ctx, const uint8_t* frames, int n_frames, i
         ctx->h2d_bytes += (unsigned long long)px * nf;
         ctx->d2h_bytes += packed ? (unsigned long long)(((size_t)px * nf + 31) / 32) * 4 : (unsigned long long)px * nf;
         CB_TRY(run_frames_device(ctx, st, s, din, dout, nf, h, w, lo, hi, nullptr, nullptr, nullptr, nullptr));
-        if (packed) {
+        if (bits_out) {
+            uint32_t* dbits = reinterpret_cast<uint32_t*>(ctx->dev_bits[s].ptr);
+            if ((px & 31) == 0) {
+                CB_TRY(launch_pack_edges(ctx, st, dout, dbits, (size_t)px * nf));           // frames are whole words: one launch
+            } else {
+                for (int f = 0; f < nf; ++f) CB_TRY(launch_pack_edges(ctx, st, dout + (size_t)f * px, dbits + (size_t)f * frame_words, (size_t)px));
+            }
+            CB_CUDA(cudaMemcpyAsync(bits_out + (size_t)f0 * frame_words, dbits, (size_t)nf * frame_words * 4, cudaMemcpyDeviceToHost, st));
+            ctx->d2h_bytes += (unsigned long long)nf * frame_words * 4 - (unsigned long long)(((size_t)px * nf + 31) / 32) * 4;
+        } else if (packed) {
             uint32_t* dbits = reinterpret_cast<uint32_t*>(ctx->dev_bits[s].ptr);
             CB_TRY(launch_pack_edges(ctx, st, dout, dbits, (size_t)px * nf));
             CB_CUDA(cudaMemcpyAsync(ctx->host_bits[s].ptr, dbits, (((size_t)px * nf + 31) / 32) * 4, cudaMemcpyDeviceToHost, st));
@@ -809,7 +824,7 @@ static int batch_host_impl(b200_ctx* ctx, const uint8_t* frames, int n_frames, i
             CB_CUDA(cudaMemcpyAsync(edges8 + (long long)f0 * px, dout, (size_t)px * nf, cudaMemcpyDeviceToHost, st));
         }
     }
-    if (packed)
+    if (packed && !bits_out)
         for (int c = std::max(0, n_chunks - (n_slots - 1)); c < n_chunks; ++c) CB_TRY(finish_chunk(c));
     for (int s = 0; s < n_slots; ++s) {
         CB_CUDA(cudaEventRecord(ctx->ev_join[s], ctx->side[s]));
@@ -838,6 +853,16 @@ int b200_canny_batch_host(b200_ctx* ctx, const uint8_t* frames, int n_frames, in
     return batch_host_impl(ctx, frames, n_frames, h, w, lo, hi, edges, nullptr, packed);
 }
 
+int b200_canny_batch_host_packed(b200_ctx* ctx, const uint8_t* frames, int n_frames, int h, int w, float sigma, int lo, int hi,
+                                 uint32_t* edge_bits) {
+    CB_TRY(check_image(frames, edge_bits, h, w));
+    CB_TRY(check_thresholds(lo, hi));
+    if (n_frames <= 0) { set_error("n_frames must be positive"); return B200_ERR_INVALID_ARG; }
+    CB_TRY(resolve_ctx(ctx));
+    CB_TRY(prepare_gauss(ctx, sigma));
+    return batch_host_impl(ctx, frames, n_frames, h, w, lo, hi, nullptr, nullptr, true, edge_bits);
+}
+
 int b200_pack_edges_device(b200_ctx* ctx, const uint8_t* d_edges, size_t n_px, uint32_t* d_bits) {
     if (!d_edges || !d_bits || n_px == 0) { set_error("bad argument to b200_pack_edges_device"); return B200_ERR_INVALID_ARG; }
     CB_TRY(resolve_ctx(ctx));
@@ -856,8 +881,18 @@ int b200_unpack_edges_host(const uint8_t* bits, size_t n_px, void* out, int elem
     return B200_OK;
 }
 
+static int profile_impl(b200_ctx* ctx, const uint8_t* d_frames, int n_frames, int h, int w, float sigma, int lo, int hi,
+                        uint8_t* d_edges, float* ms_out, int* launches_out, bool pipelined);
 int b200_profile_stages_device(b200_ctx* ctx, const uint8_t* d_frames, int n_frames, int h, int w, float sigma, int lo, int hi,
                                uint8_t* d_edges, float* ms_out, int* launches_out) {
+    return profile_impl(ctx, d_frames, n_frames, h, w, sigma, lo, hi, d_edges, ms_out, launches_out, false);
+}
+int b200_profile_pipeline_device(b200_ctx* ctx, const uint8_t* d_frames, int n_frames, int h, int w, float sigma, int lo, int hi,
+                                 uint8_t* d_edges, float* ms_out, int* launches_out) {
+    return profile_impl(ctx, d_frames, n_frames, h, w, sigma, lo, hi, d_edges, ms_out, launches_out, true);
+}
+static int profile_impl(b200_ctx* ctx, const uint8_t* d_frames, int n_frames, int h, int w, float sigma, int lo, int hi,
+                        uint8_t* d_edges, float* ms_out, int* launches_out, bool pipelined) {
     CB_TRY(check_image(d_frames, d_edges, h, w));
     CB_TRY(check_thresholds(lo, hi));
     if (!ms_out || !launches_out || n_frames <= 0) { set_error("bad argument"); return B200_ERR_INVALID_ARG; }
@@ -871,10 +906,16 @@ int b200_profile_stages_device(b200_ctx* ctx, const uint8_t* d_frames, int n_fra
     ctx->prof.recs.clear();
     ctx->prof.on = true;
     int status = B200_OK;
-    for (int f0 = 0; f0 < n_frames && status == B200_OK; f0 += chunk) {
-        const int nf = std::min(chunk, n_frames - f0);
-        status = run_frames_device(ctx, ctx->stream, 0, d_frames + (long long)f0 * px, d_edges + (long long)f0 * px, nf, h, w, lo, hi,
-                                   nullptr, nullptr, nullptr, nullptr);
+    if (pipelined) {
+        // the production path itself (three stream slots): every kernel's events sit on its own stream, so the durations
+        // include whatever the kernel shares the machine with
+        status = b200_canny_batch_device(ctx, d_frames, n_frames, h, w, sigma, lo, hi, d_edges);
+    } else {
+        for (int f0 = 0; f0 < n_frames && status == B200_OK; f0 += chunk) {
+            const int nf = std::min(chunk, n_frames - f0);
+            status = run_frames_device(ctx, ctx->stream, 0, d_frames + (long long)f0 * px, d_edges + (long long)f0 * px, nf, h, w, lo, hi,
+                                       nullptr, nullptr, nullptr, nullptr);
+        }
     }
     ctx->prof.on = false;
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
@@ -920,6 +961,17 @@ int b200_count_edges_device(b200_ctx* ctx, const uint8_t* d_edges, size_t n, uns
     unsigned long long* d = reinterpret_cast<unsigned long long*>(ctx->ws_misc.ptr);
     CB_TRY(launch_count255(ctx, ctx->stream, d_edges, n, d));
     CB_CUDA(cudaMemcpyAsync(count, d, sizeof(*count), cudaMemcpyDeviceToHost, ctx->stream));
+    CB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+
+int b200_hash_edges_device(b200_ctx* ctx, const uint8_t* d_edges, size_t n, unsigned long long global_offset, unsigned long long* hash) {
+    if (!d_edges || !hash) { set_error("null pointer"); return B200_ERR_INVALID_ARG; }
+    CB_TRY(resolve_ctx(ctx));
+    CB_TRY(ensure_ws(ctx->ws_misc, 256));
+    unsigned long long* d = reinterpret_cast<unsigned long long*>(ctx->ws_misc.ptr) + 8;
+    CB_TRY(launch_hash255(ctx, ctx->stream, d_edges, n, global_offset, d));
+    CB_CUDA(cudaMemcpyAsync(hash, d, sizeof(*hash), cudaMemcpyDeviceToHost, ctx->stream));
     CB_CUDA(cudaStreamSynchronize(ctx->stream));
     return B200_OK;
 }

@@ -117,6 +117,89 @@ __global__ void band_mark_kernel(const int32_t* __restrict__ uf, const b200_band
     if (node >= 0 && g_find(uf, node) == kSuper) parent[r] = kSuper;
 }
 
+
+// ---- the band's local stages, in pieces (b200_band_front chains them; bands_mgpu.cu interleaves them with the halo exchange) ----
+int band_prepare(b200_ctx* ctx, const BandGeom& g, float sigma) {
+    if (!g.d_rows || !g.d_edges) { set_error("null pointer"); return B200_ERR_INVALID_ARG; }
+    if (g.rows < 2 || g.width < 2 || g.height < 2 || g.row0 < 0 || g.row0 + g.rows > g.height || g.above < 0 || g.below < 0 ||
+        g.above > g.row0 || g.row0 + g.rows + g.below > g.height) {
+        set_error("inconsistent band geometry (row0=%d rows=%d halos=%d/%d height=%d)", g.row0, g.rows, g.above, g.below, g.height);
+        return B200_ERR_INVALID_ARG;
+    }
+    if ((long long)g.rows * g.width >= (1LL << 31)) { set_error("band exceeds int indexing"); return B200_ERR_UNSUPPORTED; }
+    if (!ctx) { set_error("band calls need an explicit context (they keep per-band state)"); return B200_ERR_INVALID_ARG; }
+    if (!thresholds_supported(g.lo, g.hi)) { set_error("thresholds minVal=%d > 255 >= maxVal=%d are not reproduced (src/utils.cpp:327-340)", g.lo, g.hi); return B200_ERR_UNSUPPORTED; }
+    CB_CUDA(cudaSetDevice(ctx->device));
+    CB_TRY(prepare_gauss(ctx, sigma));
+    const int need = ctx->gauss.radius + 2;
+    const int need_above = need < g.row0 ? need : g.row0;
+    const int rows_after = g.height - (g.row0 + g.rows);
+    const int need_below = need < rows_after ? need : rows_after;
+    if (g.above < need_above || g.below < need_below) {
+        set_error("band needs %d/%d halo rows above/below (got %d/%d)", need_above, need_below, g.above, g.below);
+        return B200_ERR_INVALID_ARG;
+    }
+    const long long px = (long long)g.rows * g.width;
+    CB_TRY(ensure_ws(ctx->ws_band_parent, (size_t)px * 4));
+    CB_TRY(ensure_ws(ctx->ws_band_list, 64 + (size_t)px * 4));
+    // the list's counter block is zero here: zeroed at allocation and retired by the previous band's kernels (HystParams::ctr);
+    // only a band that failed between its front launches and its labelling leaves it dirty
+    if (ctx->list_dirty[3]) CB_CUDA(cudaMemsetAsync(ctx->ws_band_list.ptr, 0, 64, ctx->stream));
+    ctx->list_dirty[3] = false;
+    return B200_OK;
+}
+
+// stages 1-3 for the band's rows [sub_row0, sub_row0 + sub_rows) (global numbers); several calls may cover one band: they append
+// to the same weak-pixel list, which band_label() then consumes
+int band_front_rows(b200_ctx* ctx, cudaStream_t st, const BandGeom& g, int sub_row0, int sub_rows) {
+    if (sub_rows <= 0) return B200_OK;
+    const long long px = (long long)g.rows * g.width;
+    FrontParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.in = g.d_rows;
+    fp.in_frame_stride = (long long)(g.above + g.rows + g.below) * g.width;
+    fp.in_row0 = g.row0 - g.above;
+    fp.in_rows = g.above + g.rows + g.below;
+    fp.width = g.width; fp.height = g.height;
+    fp.out_row0 = sub_row0; fp.out_rows = sub_rows; fp.plane_row0 = g.row0; fp.n_frames = 1;
+    fp.cls = g.d_edges; fp.out_frame_stride = px;
+    fp.w = ctx->gauss.d_w; fp.count = ctx->gauss.d_count; fp.radius = ctx->gauss.radius;
+    fill_thresholds(fp, g.lo, g.hi);
+    fp.parent = reinterpret_cast<int32_t*>(ctx->ws_band_parent.ptr);
+    fp.kept_count = reinterpret_cast<unsigned int*>(ctx->ws_band_list.ptr);
+    fp.kept_list = reinterpret_cast<uint32_t*>(ctx->ws_band_list.ptr) + 16;
+    ctx->list_dirty[3] = true;   // until band_label() has consumed the list
+    bool sparse = false;
+    CB_TRY(launch_front(ctx, st, fp, &sparse));
+    ctx->band_front_sparse = sparse;
+    return B200_OK;
+}
+
+// band-local connected components over the weak pixels the front launches listed (or the whole plane)
+int band_label(b200_ctx* ctx, cudaStream_t st, const BandGeom& g) {
+    const long long px = (long long)g.rows * g.width;
+    const unsigned int prev_kept = *reinterpret_cast<volatile unsigned int*>(&ctx->h_kept[3]);   // previous band on this context
+    const bool dense = ctx->kept_px[3] > 0 && (long long)prev_kept * 8 > ctx->kept_px[3];
+    const bool front_sparse = ctx->band_front_sparse;
+    if (front_sparse) ctx->kept_px[3] = px;
+    const bool sparse = front_sparse && !dense;
+    ctx->band_sparse = sparse;
+    HystParams hp;
+    memset(&hp, 0, sizeof(hp));
+    unsigned int* ctr = reinterpret_cast<unsigned int*>(ctx->ws_band_list.ptr);
+    hp.list = sparse ? reinterpret_cast<const uint32_t*>(ctr + 16) : nullptr;
+    hp.ctr = front_sparse ? ctr : nullptr;
+    hp.h_kept = ctx->d_kept + 3;
+    hp.kept_prev = prev_kept;
+    hp.kept_thresh = (unsigned int)(px / 8);
+    hp.cls = g.d_edges; hp.parent = reinterpret_cast<int32_t*>(ctx->ws_band_parent.ptr);
+    hp.frame_stride = px; hp.rows = g.rows; hp.width = g.width; hp.row0 = g.row0; hp.n_frames = 1;
+    CB_TRY(launch_ccl_label(ctx, st, hp));
+    ctx->list_dirty[3] = false;
+    ctx->band_rows = g.rows; ctx->band_width = g.width; ctx->band_row0 = g.row0; ctx->band_cls = g.d_edges;
+    return B200_OK;
+}
+
 }  // namespace cb
 
 using namespace cb;
@@ -128,68 +211,10 @@ int b200_band_record_count(int width) { return band_records(width); }
 
 int b200_band_front(b200_ctx* ctx, const uint8_t* d_rows, int halo_above, int halo_below, int band_rows, int row0,
                     int global_height, int width, float sigma, int lo, int hi, uint8_t* d_edges) {
-    if (!d_rows || !d_edges) { set_error("null pointer"); return B200_ERR_INVALID_ARG; }
-    if (band_rows < 2 || width < 2 || global_height < 2 || row0 < 0 || row0 + band_rows > global_height || halo_above < 0 ||
-        halo_below < 0 || halo_above > row0 || row0 + band_rows + halo_below > global_height) {
-        set_error("inconsistent band geometry (row0=%d rows=%d halos=%d/%d height=%d)", row0, band_rows, halo_above, halo_below,
-                  global_height);
-        return B200_ERR_INVALID_ARG;
-    }
-    if ((long long)band_rows * width >= (1LL << 31)) { set_error("band exceeds int indexing"); return B200_ERR_UNSUPPORTED; }
-    if (!ctx) { set_error("band calls need an explicit context (they keep per-band state)"); return B200_ERR_INVALID_ARG; }
-    if (!thresholds_supported(lo, hi)) { set_error("thresholds minVal=%d > 255 >= maxVal=%d are not reproduced (src/utils.cpp:327-340)", lo, hi); return B200_ERR_UNSUPPORTED; }
-    CB_CUDA(cudaSetDevice(ctx->device));
-    CB_TRY(prepare_gauss(ctx, sigma));
-    const int need = ctx->gauss.radius + 2;
-    const int need_above = need < row0 ? need : row0;
-    const int rows_after = global_height - (row0 + band_rows);
-    const int need_below = need < rows_after ? need : rows_after;
-    if (halo_above < need_above || halo_below < need_below) {
-        set_error("band needs %d/%d halo rows above/below (got %d/%d)", need_above, need_below, halo_above, halo_below);
-        return B200_ERR_INVALID_ARG;
-    }
-    const long long px = (long long)band_rows * width;
-    CB_TRY(ensure_ws(ctx->ws_band_parent, (size_t)px * 4));
-    CB_TRY(ensure_ws(ctx->ws_band_list, 64 + (size_t)px * 4));
-    cudaStream_t st = ctx->stream;
-    FrontParams fp;
-    memset(&fp, 0, sizeof(fp));
-    fp.in = d_rows;
-    fp.in_frame_stride = (long long)(halo_above + band_rows + halo_below) * width;
-    fp.in_row0 = row0 - halo_above;
-    fp.in_rows = halo_above + band_rows + halo_below;
-    fp.width = width; fp.height = global_height;
-    fp.out_row0 = row0; fp.out_rows = band_rows; fp.n_frames = 1;
-    fp.cls = d_edges; fp.out_frame_stride = px;
-    fp.w = ctx->gauss.d_w; fp.count = ctx->gauss.d_count; fp.radius = ctx->gauss.radius;
-    fill_thresholds(fp, lo, hi);
-    fp.parent = reinterpret_cast<int32_t*>(ctx->ws_band_parent.ptr);
-    fp.kept_count = reinterpret_cast<unsigned int*>(ctx->ws_band_list.ptr);
-    fp.kept_list = reinterpret_cast<uint32_t*>(ctx->ws_band_list.ptr) + 16;
-    // the list's counter block is zero here (zeroed at allocation, retired by the previous band's kernels: HystParams::ctr)
-    if (ctx->list_dirty[3]) CB_CUDA(cudaMemsetAsync(fp.kept_count, 0, 64, st));
-    ctx->list_dirty[3] = true;
-    bool sparse = false;
-    CB_TRY(launch_front(ctx, st, fp, &sparse));
-    const unsigned int prev_kept = *reinterpret_cast<volatile unsigned int*>(&ctx->h_kept[3]);   // previous band on this context
-    const bool dense = ctx->kept_px[3] > 0 && (long long)prev_kept * 8 > ctx->kept_px[3];
-    if (sparse) ctx->kept_px[3] = px;
-    const bool front_sparse = sparse;
-    sparse = sparse && !dense;
-    ctx->band_sparse = sparse;
-    HystParams hp;
-    memset(&hp, 0, sizeof(hp));
-    hp.list = sparse ? fp.kept_list : nullptr;
-    hp.ctr = front_sparse ? fp.kept_count : nullptr;
-    hp.h_kept = ctx->d_kept + 3;
-    hp.kept_prev = prev_kept;
-    hp.kept_thresh = (unsigned int)(px / 8);
-    hp.cls = d_edges; hp.parent = reinterpret_cast<int32_t*>(ctx->ws_band_parent.ptr);
-    hp.frame_stride = px; hp.rows = band_rows; hp.width = width; hp.row0 = row0; hp.n_frames = 1;
-    CB_TRY(launch_ccl_label(ctx, st, hp));
-    ctx->list_dirty[3] = false;
-    ctx->band_rows = band_rows; ctx->band_width = width; ctx->band_row0 = row0; ctx->band_cls = d_edges;
-    return B200_OK;
+    BandGeom g{d_rows, halo_above, halo_below, band_rows, row0, global_height, width, lo, hi, d_edges};
+    CB_TRY(band_prepare(ctx, g, sigma));
+    CB_TRY(band_front_rows(ctx, ctx->stream, g, row0, band_rows));
+    return band_label(ctx, ctx->stream, g);
 }
 
 int b200_band_boundary_export(b200_ctx* ctx, int band_rows, int width, b200_band_record* d_records) {

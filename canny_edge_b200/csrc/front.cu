@@ -305,7 +305,7 @@ front_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
                 s_blur[((gy + kBias) & (kRingCap - 1)) * kBlurPitch + c] = (int16_t)bi;
                 if (SPILL) {
                     if (p.blur && gy >= yb && gy < ye && c >= 2 && c < 2 + kTW && gx < W)
-                        p.blur[(long long)frame * p.out_frame_stride + (long long)(gy - p.out_row0) * W + gx] = (int16_t)bi;
+                        p.blur[(long long)frame * p.out_frame_stride + (long long)(gy - p.plane_row0) * W + gx] = (int16_t)bi;
                 }
             }
         }
@@ -418,7 +418,7 @@ front_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
                         cls_word |= (uint32_t)cls << (8 * e);
                         if (SPILL) { magv[e] = (int16_t)mag; angv[e] = (int16_t)(dir * 45); nmsv[e] = keep ? (int16_t)mag : (int16_t)0; }
                     }
-                    const long long o = (long long)frame * p.out_frame_stride + (long long)(y - p.out_row0) * W + xw;
+                    const long long o = (long long)frame * p.out_frame_stride + (long long)(y - p.plane_row0) * W + xw;
                     if (((W & 3) == 0) && xw + 3 < W) {
                         *reinterpret_cast<uint32_t*>(p.cls + o) = cls_word;
                     } else {

@@ -423,7 +423,7 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
                 int q = cq_lo + ((warp - cq_lo) & 7);         // first class row of this warp (rows q = warp mod 8)
                 const int32_t* vrow = s_vu + q * kVuPitch + 4 * lane;
                 int32_t* nrow = s_np + q * kNpPitch + 4 * lane;
-                uint8_t* o = p.cls + (long long)frame * p.out_frame_stride + (long long)(y_base + q - 1 - p.out_row0) * W + (x0 + 4 * lane);
+                uint8_t* o = p.cls + (long long)frame * p.out_frame_stride + (long long)(y_base + q - 1 - p.plane_row0) * W + (x0 + 4 * lane);
                 int ent = ((q - 1) << 6) | (lane << 1);
                 const long long o_step = 8LL * W;
                 // two copies of the loop so the store form is decided once, not per row: the aligned 32-bit store (every strip of
@@ -462,7 +462,7 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
 
         // ===================== phase 3b: direction, NMS and thresholds for the candidates only =====================
         {
-            const long long out_off = (long long)frame * p.out_frame_stride + (long long)(y_base - p.out_row0) * W + (x0 - 2) + 1;
+            const long long out_off = (long long)frame * p.out_frame_stride + (long long)(y_base - p.plane_row0) * W + (x0 - 2) + 1;
             uint8_t* out_base = p.cls + out_off;
             int32_t* par_base = p.parent + out_off;                           // only dereferenced when `sparse`
             const int idx_base = (int)out_off;                                // launch-relative pixel index of (class row 0, column j = 1)
@@ -548,7 +548,7 @@ front2_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
             if (total && lane == 0) pend_base = atomicAdd(p.kept_count, (unsigned int)total);
             pend_off = incl - cnt;
             // word tid <-> class row rr = tid >> 2, columns 32*(tid & 3) .. of the strip
-            pend_g0 = (int)((long long)frame * p.out_frame_stride + (long long)(y_base + (tid >> 2) - p.out_row0) * W + x0 + 32 * (tid & 3));
+            pend_g0 = (int)((long long)frame * p.out_frame_stride + (long long)(y_base + (tid >> 2) - p.plane_row0) * W + x0 + 32 * (tid & 3));
         }
         // VU rows 64,65 (blurred-row neighbours of the next slab's first class rows) -> rows 0,1
         if (k + 1 < n_slabs) s_vu[(tid >> 7) * kVuPitch + (tid & 127)] = s_vu[(kSlab + (tid >> 7)) * kVuPitch + (tid & 127)];

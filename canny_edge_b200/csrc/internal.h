@@ -56,7 +56,10 @@ struct FrontParams {
     int width;              // image width == pitch of every plane
     int height;             // GLOBAL image height (border rules key off this)
     int out_row0;           // first global row this launch produces
-    int out_rows;           // number of rows produced (planes below are indexed from out_row0)
+    int out_rows;           // number of rows produced
+    int plane_row0;         // global row of row 0 of every OUTPUT plane below (cls, parent, spill planes).  == out_row0 unless a launch
+                            // produces only part of the plane's rows (row bands: interior rows first, the rows that need the
+                            // neighbours' halo once it has arrived; bands_mgpu.cu)
     int n_frames;
     uint8_t* cls;           // out: class map (0 / 1 weak / 255 strong), out_rows*width per frame
     long long out_frame_stride;  // elements between frames in every output plane
@@ -176,6 +179,7 @@ struct b200_ctx {
     int band_rows = 0, band_width = 0, band_row0 = 0;
     uint8_t* band_cls = nullptr;          // class map of the resident band (caller's d_edges)
     bool band_sparse = false;             // the resident band's labels were built from the kept-pixel list
+    bool band_front_sparse = false;       // the band's front launches produced the kept-pixel list
     // weak-pixel count of the last launch of each pipeline slot, copied back asynchronously (pinned host memory, never waited
     // for): when more than 1/8 of the previous launch's pixels were weak the next one uses the tile-based labelling, whose shared-
     // memory unions win on such maps.  Both give identical results; a stale value only costs speed.
@@ -232,9 +236,22 @@ int launch_sobel(b200_ctx* ctx, cudaStream_t st, const int16_t* blur, int h, int
 int launch_nonmaximal(b200_ctx* ctx, cudaStream_t st, const int16_t* mag, const int16_t* ang, int h,
                       int w, int16_t* out);
 int launch_bgr_to_gray(b200_ctx* ctx, cudaStream_t st, const uint8_t* bgr, uint8_t* gray, size_t n_px);
+// band.cu: one row band's local stages in pieces
+struct BandGeom {
+    const uint8_t* d_rows;   // global row (row0 - above) of the band buffer
+    int above, below;        // halo rows present above / below the band
+    int rows, row0;          // rows owned, first global row
+    int height, width;       // GLOBAL image height, width
+    int lo, hi;
+    uint8_t* d_edges;        // rows x width class / edge map of the band
+};
+int band_prepare(b200_ctx* ctx, const BandGeom& g, float sigma);
+int band_front_rows(b200_ctx* ctx, cudaStream_t st, const BandGeom& g, int sub_row0, int sub_rows);
+int band_label(b200_ctx* ctx, cudaStream_t st, const BandGeom& g);
 // synth.cu
 int launch_synth(b200_ctx* ctx, cudaStream_t st, uint8_t* d, int n_frames, int row0, int rows, int width,
                  int kind, uint64_t seed, int first_frame);
 int launch_count255(b200_ctx* ctx, cudaStream_t st, const uint8_t* d, size_t n, unsigned long long* d_count);
+int launch_hash255(b200_ctx* ctx, cudaStream_t st, const uint8_t* d, size_t n, unsigned long long offset, unsigned long long* d_out);
 
 }  // namespace cb

@@ -33,6 +33,27 @@ __global__ void count255_kernel(const uint8_t* __restrict__ d, size_t n, unsigne
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, local);
 }
 
+// Position-dependent checksum of an edge map: sum over edge pixels of mix64(global pixel index), mod 2^64.  A sum, so the checksums
+// of the row bands of one image (each computed on its own GPU with its global offset) add up to the checksum of the whole image.
+__global__ void hash255_kernel(const uint8_t* __restrict__ d, size_t n, unsigned long long offset, unsigned long long* __restrict__ out) {
+    unsigned long long local = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        if (d[i] == 255) local += mix64(offset + i);
+    for (int off = 16; off; off >>= 1) local += __shfl_down_sync(0xffffffffu, local, off);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, local);
+}
+int launch_hash255(b200_ctx* ctx, cudaStream_t st, const uint8_t* d, size_t n, unsigned long long offset, unsigned long long* d_out) {
+    CB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(unsigned long long), st));
+    size_t blocks = (n + 1023) / 1024;
+    const size_t cap = 32 * (size_t)(ctx->sm_count > 0 ? ctx->sm_count : 148);
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    hash255_kernel<<<(int)blocks, 256, 0, st>>>(d, n, offset, d_out);
+    CB_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return B200_OK;
+}
+
 int launch_synth(b200_ctx* ctx, cudaStream_t st, uint8_t* d, int n_frames, int row0, int rows, int width, int kind,
                  uint64_t seed, int first_frame) {
     const long long total = (long long)rows * width * n_frames;

@@ -10,10 +10,15 @@ Two ways the path shards (the reference itself is single-GPU, single-
      2. hysteresis label merge: every band exports its first/last row as (label, flags) records
         (`b200_band_boundary_export`), ONE all-gather (`gather_records`), then every rank unions the records
         that touch across a boundary and finalises its own band (`b200_band_finalize`).
-  `BandPipeline.run` chains: exchange_halos -> b200_band_front -> export -> all_gather -> finalize.
+  Both steps now live in C (`b200_bands_*`, csrc/bands_mgpu.cu: copy-engine halo pulls over NVLink peer mappings + sparse
+  boundary records read from peer memory, or NCCL send/recv + all-gather); `BandPipeline` is a thin caller of that handle and
+  torch.distributed only carries the 128-byte NCCL unique id at creation.  `TorchBandPipeline` is the round-1 form (the two
+  exchanges as torch.distributed calls around b200_band_front / _boundary_export / _finalize), kept as a cross-check and because
+  its exchange helpers are device-agnostic (the CPU tests run them over gloo).
 
-`canny_bands_virtual` runs the same band kernels for G bands sequentially on ONE GPU (exchange replaced by
-local slicing/concatenation), so the cross-band merge is testable without a multi-GPU box.
+`canny_bands_virtual` runs G bands of one image as an in-process group on ONE GPU through the same C pipeline
+(`b200_bands_create_group`: peers are plain pointers), so halo pulls, flags and the cross-band merge are testable without a
+multi-GPU box.
 
 All compute is in libcanny_b200.so (sm_100a CUDA); nothing here computes pixels on the CPU.
 """
@@ -119,8 +124,8 @@ def gather_records(records, world: int, group=None):
 # ---------------------------------------------------------------------------------------------------
 # band pipeline on one rank
 # ---------------------------------------------------------------------------------------------------
-class BandPipeline:
-    """Canny of one row band of a larger image on this rank's GPU.
+class TorchBandPipeline:
+    """(Round-1 form: exchanges through torch.distributed.)  Canny of one row band of a larger image on this rank's GPU.
 
     The pipeline owns ONE persistent device buffer [halo above | band | halo below] (`buffer`), so a step neither allocates nor
     copies the band: callers that produce their rows on the device write them straight into `band_view()`; `run(band)` with an
@@ -233,7 +238,129 @@ class BandPipeline:
         return edges
 
 
-def canny_bands_virtual(img: np.ndarray, n_bands: int, sigma: float, min_val: int, max_val: int, device: int = 0) -> np.ndarray:
+STAGES = ("signal+interior", "halo_wait", "edges+label", "export", "record_exchange", "finalize")
+TRANSPORTS = {0: "single band", 1: "p2p (copy-engine halo pulls + sparse records over NVLink peer mappings)", 2: "nccl (send/recv + all-gather)"}
+
+
+class BandPipeline:
+    """One rank's band of a larger image through the C pipeline (b200_bands_*).  The handle owns the persistent
+    [halo | band | halo] buffer: write the rank's rows into `band_view()` and call `run()`.
+
+    world > 1: torch.distributed must be initialised; it only broadcasts the NCCL unique id the C side builds its communicator from."""
+
+    def __init__(self, ctx: Context, height: int, width: int, rank: int, world: int, sigma: float, min_val: int,
+                 max_val: int, group=None):
+        import torch
+
+        self.ctx, self.lib = ctx, load()
+        self.geo = band_geometry(height, width, rank, world, sigma)
+        self.handle = C.c_void_p()
+        uid = None
+        if world > 1:
+            import torch.distributed as dist
+
+            raw = (C.c_ubyte * 128)()
+            if rank == 0:
+                check(self.lib.b200_bands_unique_id(raw))
+            t = torch.tensor(list(raw), dtype=torch.uint8)
+            if dist.get_backend(group) == "nccl":
+                t = t.cuda(ctx.device)
+            dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            uid = (C.c_ubyte * 128)(*t.cpu().tolist())
+        check(self.lib.b200_bands_create(ctx.handle, None, uid, rank, world, height, width, C.c_float(sigma), int(min_val),
+                                         int(max_val), C.byref(self.handle)))
+        r0, rows, halo, tr = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        check(self.lib.b200_bands_info(self.handle, C.byref(r0), C.byref(rows), C.byref(halo), C.byref(tr)))
+        assert (r0.value, rows.value, halo.value) == (self.geo.row0, self.geo.rows, self.geo.halo)
+        self.transport = tr.value
+        self.timings = None
+
+    def band_view(self, device=None):
+        """(rows, W) uint8 CUDA tensor aliasing the band's own rows inside the handle's buffer."""
+        ptr = C.c_void_p()
+        check(self.lib.b200_bands_input(self.handle, C.byref(ptr)))
+        return _tensor_from_ptr(ptr.value, (self.geo.rows, self.geo.width), self.ctx.device)
+
+    def run(self, band=None, edges=None):
+        import torch
+
+        g = self.geo
+        self.ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        if edges is None:
+            edges = torch.empty((g.rows, g.width), dtype=torch.uint8, device=torch.device("cuda", self.ctx.device))
+        if band is not None:
+            self.band_view().copy_(band)
+        check(self.lib.b200_bands_set_timing(self.handle, 1 if self.timings is not None else 0))
+        check(self.lib.b200_bands_run(self.handle, edges.data_ptr()))
+        if self.timings is not None:
+            ms = (C.c_float * 6)()
+            check(self.lib.b200_bands_stage_ms(self.handle, ms))
+            for name, v in zip(STAGES, ms):
+                self.timings[name] = self.timings.get(name, 0.0) + float(v)
+        return edges
+
+    def check(self):
+        check(self.lib.b200_bands_check(self.handle))
+
+    def close(self):
+        if self.handle:
+            check(self.lib.b200_bands_destroy(self.handle))
+            self.handle = C.c_void_p()
+
+
+def _tensor_from_ptr(ptr: int, shape, device: int):
+    """uint8 CUDA tensor over existing device memory (no copy, no ownership) via __cuda_array_interface__."""
+    import torch
+
+    class _Mem:
+        pass
+
+    m = _Mem()
+    m.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "|u1", "data": (int(ptr), False), "version": 3, "strides": None}
+    return torch.as_tensor(m, device=torch.device("cuda", device))
+
+
+def canny_bands_virtual(img: np.ndarray, n_bands: int, sigma: float, min_val: int, max_val: int, device: int = 0,
+                        steps: int = 1) -> np.ndarray:
+    """All bands of one image as an in-process group on ONE GPU (one context per band) through b200_bands_run_group: the same halo
+    pulls, ready flags, split front launches, sparse record exchange and cross-band merge as the multi-GPU run, with plain
+    pointers in place of IPC mappings.  Returns the (H, W) uint8 0/255 map."""
+    import torch
+
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    H, W = img.shape
+    dev = torch.device("cuda", device)
+    lib = load()
+    ctxs: List[Context] = [Context(device) for _ in range(n_bands)]
+    handles = (C.c_void_p * n_bands)()
+    try:
+        check(lib.b200_bands_create_group((C.c_void_p * n_bands)(*[c.handle for c in ctxs]), n_bands, H, W, C.c_float(sigma),
+                                          int(min_val), int(max_val), handles))
+        d_img = torch.from_numpy(img).to(dev)
+        edges = []
+        for b in range(n_bands):
+            r0, rows = C.c_int(), C.c_int()
+            check(lib.b200_bands_info(handles[b], C.byref(r0), C.byref(rows), None, None))
+            ptr = C.c_void_p()
+            check(lib.b200_bands_input(handles[b], C.byref(ptr)))
+            _tensor_from_ptr(ptr.value, (rows.value, W), device).copy_(d_img[r0.value:r0.value + rows.value])
+            edges.append(torch.empty((rows.value, W), dtype=torch.uint8, device=dev))
+        torch.cuda.synchronize(dev)   # the copies ran on torch's stream; the bands work on their contexts' streams
+        e_ptrs = (C.c_void_p * n_bands)(*[e.data_ptr() for e in edges])
+        for _ in range(steps):
+            check(lib.b200_bands_run_group(handles, n_bands, e_ptrs))
+        for b in range(n_bands):
+            check(lib.b200_bands_check(handles[b]))
+        return torch.cat(edges).cpu().numpy()
+    finally:
+        for h in handles:
+            if h:
+                lib.b200_bands_destroy(h)
+        for c in ctxs:
+            c.close()
+
+
+def canny_bands_virtual_torch(img: np.ndarray, n_bands: int, sigma: float, min_val: int, max_val: int, device: int = 0) -> np.ndarray:
     """All bands of one image on ONE GPU, sequentially, through the same band kernels (one context per band,
     because a context keeps its band's label state between front/export/finalize).  The two exchanges become
     local slicing and concatenation.  Returns the (H, W) uint8 0/255 map."""
@@ -245,7 +372,7 @@ def canny_bands_virtual(img: np.ndarray, n_bands: int, sigma: float, min_val: in
     d_img = torch.from_numpy(img).to(dev)
     ctxs: List[Context] = [Context(device) for _ in range(n_bands)]
     try:
-        pipes = [BandPipeline(ctxs[b], H, W, b, n_bands, sigma, min_val, max_val) for b in range(n_bands)]
+        pipes = [TorchBandPipeline(ctxs[b], H, W, b, n_bands, sigma, min_val, max_val) for b in range(n_bands)]
         edges, recs = [], []
         for p in pipes:
             g = p.geo

@@ -157,6 +157,13 @@ int b200_bgr_to_gray_device(b200_ctx* ctx, const uint8_t* d_bgr, size_t n_px, ui
 int b200_canny_batch_host(b200_ctx* ctx, const uint8_t* frames, int n_frames, int height, int width,
                           float sigma, int min_val, int max_val, uint8_t* edges);
 
+/* Same, but the caller takes the maps in the PACKED form they cross PCIe in: 1 bit per pixel, bit i of frame f's words <-> pixel
+ * i of frame f, every frame starting on a 32-bit word (frame stride ceil(height*width/32) words).  No host expansion pass: on a
+ * host whose memory system is shared by several GPUs' transfers this is the scalable form (b200_unpack_edges_host expands a
+ * frame when bytes are needed after all). */
+int b200_canny_batch_host_packed(b200_ctx* ctx, const uint8_t* frames, int n_frames, int height, int width,
+                                 float sigma, int min_val, int max_val, uint32_t* edge_bits);
+
 /* Same with DEVICE pointers (already resident in HBM): d_frames and d_edges are n_frames*height*width
  * bytes each, on the context's device.  Asynchronous on the context's stream.  d_edges may not alias
  * d_frames. */
@@ -180,6 +187,12 @@ int b200_unpack_edges_host(const uint8_t* bits, size_t n_px, void* out, int elem
 int b200_profile_stages_device(b200_ctx* ctx, const uint8_t* d_frames, int n_frames, int height,
                                int width, float sigma, int min_val, int max_val, uint8_t* d_edges,
                                float* ms_out, int* launches_out);
+
+/* Same, but through the production path itself (b200_canny_batch_device: three stream slots whose kernels overlap), every
+ * kernel bracketed by events on ITS stream: durations of kernels as they run in the timed bench step, sharing the machine. */
+int b200_profile_pipeline_device(b200_ctx* ctx, const uint8_t* d_frames, int n_frames, int height,
+                                 int width, float sigma, int min_val, int max_val, uint8_t* d_edges,
+                                 float* ms_out, int* launches_out);
 
 /* ------------------------------------------------------------------ row-band sharding ---------- */
 
@@ -216,6 +229,59 @@ int b200_band_boundary_export(b200_ctx* ctx, int band_rows, int width, b200_band
 int b200_band_finalize(b200_ctx* ctx, const b200_band_record* d_all_records, int n_bands,
                        int band_index, int band_rows, int width, uint8_t* d_edges);
 
+/* ------------------------------------------------------------------ row bands across GPUs ------- */
+
+/* The whole band pipeline of one rank — halo exchange, stages 1-3, band-local labelling, boundary-record exchange, cross-band
+ * merge, finalisation — behind one handle, for a caller in the position of src/main.cpp:128 that owns several B200s (the
+ * reference itself is single-GPU and finishes hysteresis on the CPU, src/cuda.cu:436).  One band per GPU, band r of `world` owns
+ * global rows [r*H/world ..) (remainder rows go to the low ranks; b200_bands_info tells).
+ *
+ * Transports (same results; b200_bands_info reports which one is active):
+ *   1 = P2P: the neighbours' band buffers are mapped (CUDA IPC between processes, plain pointers inside one process); halo rows
+ *       are pulled by the copy engines over NVLink while the front kernel works on the interior rows, and the boundary records
+ *       travel sparse (candidate pixels only), read straight from the peers' memory by the merge kernel.  No collective on the
+ *       data path; NCCL only bootstraps (all-gather of the IPC handles).
+ *   2 = NCCL: ncclSend/ncclRecv of the halo rows + one ncclAllGather of the dense records.  Chosen when a peer cannot be mapped,
+ *       or with B200_BANDS_TRANSPORT=nccl in the environment.
+ *   0 = a single band (world == 1): no exchange.
+ *
+ * b200_bands_create: one call per rank (one process per GPU, or one thread per GPU with separate communicators).  Pass EITHER
+ *   an existing ncclComm_t of exactly `world` ranks (of the libnccl.so.2 already loaded in the process: the library resolves NCCL
+ *   with dlopen and has no link-time dependency on it) OR nccl_comm = NULL and the 128-byte unique id that rank 0 obtained from
+ *   b200_bands_unique_id and the caller broadcast by its own means (MPI, a socket, torch.distributed ...).  Collective: every rank
+ *   must call it.  world == 1 needs neither.
+ * b200_bands_create_group: all bands inside ONE process (ctxs[i] may sit on different devices, peer access is enabled, or on the
+ *   same device: the virtual-band mode of the tests); no NCCL at all.  Drive a group with b200_bands_run_group.
+ * b200_bands_input: device pointer of the band's own rows inside the handle's persistent [halo | band | halo] buffer: the caller
+ *   writes its rows (rows x width bytes) there, on the context's stream or ordered before it, then calls run.
+ * b200_bands_run: one step, asynchronous on the context's stream; d_edges (rows x width bytes, device) holds the band's 0 / 255
+ *   map afterwards.  Collective: every rank calls it the same number of times.  A rank may overwrite its input rows again as soon
+ *   as ITS step has completed (every peer has fetched what it needs by then).
+ * b200_bands_check: synchronises and reports a peer that never signalled (bounded waits in the kernels) as B200_ERR_CUDA.
+ * b200_bands_set_timing / b200_bands_stage_ms: CUDA-event times (ms) of the last step's stages on this rank:
+ *   [0] signal + interior rows, [1] waiting for the halo rows, [2] edge rows + labelling, [3] record export, [4] record exchange,
+ *   [5] cross-band merge + finalisation.
+ */
+typedef struct b200_bands b200_bands;
+#define B200_NCCL_UNIQUE_ID_BYTES 128
+int b200_bands_unique_id(void* id_out /* B200_NCCL_UNIQUE_ID_BYTES */);
+int b200_bands_create(b200_ctx* ctx, void* nccl_comm, const void* unique_id, int rank, int world, int height, int width,
+                      float sigma, int min_val, int max_val, b200_bands** out);
+int b200_bands_create_group(b200_ctx* const* ctxs, int n_bands, int height, int width, float sigma, int min_val, int max_val,
+                            b200_bands** out /* n_bands handles */);
+int b200_bands_destroy(b200_bands* bands);
+int b200_bands_info(const b200_bands* bands, int* row0, int* rows, int* halo_rows, int* transport);
+int b200_bands_input(b200_bands* bands, uint8_t** d_band_rows);
+int b200_bands_run(b200_bands* bands, uint8_t* d_edges);
+int b200_bands_run_group(b200_bands* const* bands, int n_bands, uint8_t* const* d_edges);
+/* the three phases b200_bands_run chains (exported for callers that interleave several bands themselves) */
+int b200_bands_begin(b200_bands* bands, uint8_t* d_edges);
+int b200_bands_front(b200_bands* bands);
+int b200_bands_finish(b200_bands* bands);
+int b200_bands_check(b200_bands* bands);
+int b200_bands_set_timing(b200_bands* bands, int on);
+int b200_bands_stage_ms(b200_bands* bands, float* ms6);
+
 /* ------------------------------------------------------------------ synthetic workloads -------- */
 
 /* Procedural test frames (pure integer hash; identical bytes on host and device) used by bench.py
@@ -249,6 +315,12 @@ int b200_division_mode_device(b200_ctx* ctx, float sigma, int* mode);
 
 /* Device-side count of 255 bytes in a u8 buffer (edge pixels), written to *count. */
 int b200_count_edges_device(b200_ctx* ctx, const uint8_t* d_edges, size_t n, unsigned long long* count);
+
+/* Position-dependent checksum of a device edge map: sum over its 255-pixels of mix64(global_offset + index) mod 2^64 (the
+ * splitmix64 finaliser of the frame generator).  Additive: the checksums of the row bands of one image, each taken with its
+ * band's global pixel offset, sum to the checksum of the whole map (bench.py's cross-GPU parity field). */
+int b200_hash_edges_device(b200_ctx* ctx, const uint8_t* d_edges, size_t n, unsigned long long global_offset,
+                           unsigned long long* hash);
 
 /* Raw device memory helpers so non-CUDA hosts (ctypes, cgo, JNI) can stage data without a CUDA
  * binding of their own. */

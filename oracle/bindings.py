@@ -128,6 +128,34 @@ class Oracle(_Base):
         return (*planes, edges) if steps else edges
 
 
+def synth_frames(n_frames: int, height: int, width: int, kind: int = 0, seed: int = 1234, first_frame: int = 0, threads: int = 1) -> np.ndarray:
+    """The bench's procedural frames from the ORACLE's own generator (oracle_synth_rows): no product code involved."""
+    import threading
+
+    if not ORACLE_LIB.exists():
+        build()
+    lib = C.CDLL(str(ORACLE_LIB))
+    lib.oracle_synth_rows.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int]
+    out = np.empty((n_frames, height, width), np.uint8)
+    jobs = list(range(n_frames))
+    lock = threading.Lock()
+
+    def work():
+        while True:
+            with lock:
+                if not jobs:
+                    return
+                f = jobs.pop()
+            lib.oracle_synth_rows(C.c_void_p(out[f].ctypes.data), 0, height, width, kind, seed, first_frame + f)
+
+    ts = [threading.Thread(target=work) for _ in range(max(1, min(threads, n_frames)))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    return out
+
+
 class Ref(_Base):
     prefix = "ref_"
 

@@ -291,3 +291,49 @@ double oracle_canny(const uint8_t* img, float sigma, int lo, int hi, int h, int 
     free(nms);
     return secs;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Workload generator (NOT part of the reference): the bench's procedural frames, so that bench.py's
+ * CPU legs (`--impl reference`, cpu_baseline) build their inputs without loading the product library.
+ * Same pure-integer hash as canny_edge_b200/csrc/canny_math.h::synth_pixel;
+ * tests/test_oracle.py checks the two generators byte for byte.
+ * kind: 0 "shapes", 1 uniform noise, 2 constant 128.
+ * ---------------------------------------------------------------------------------------------- */
+static uint64_t o_mix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+static uint64_t o_hash4(uint64_t seed, uint64_t f, uint64_t a, uint64_t b) {
+    return o_mix64(o_mix64(o_mix64(o_mix64(seed) ^ f) ^ a) ^ b);
+}
+static uint8_t o_synth_pixel(int kind, uint64_t seed, int frame, int x, int y) {
+    if (kind == 2) return 128;
+    if (kind == 1) return (uint8_t)(o_hash4(seed ^ 0x7015Eull, (uint64_t)frame, (uint64_t)x, (uint64_t)y) & 255);
+    int X = x >> 8, Y = y >> 8, fx = x & 255, fy = y & 255;
+    int v00 = (int)(o_hash4(seed, frame, X, Y) & 127), v10 = (int)(o_hash4(seed, frame, X + 1, Y) & 127);
+    int v01 = (int)(o_hash4(seed, frame, X, Y + 1) & 127), v11 = (int)(o_hash4(seed, frame, X + 1, Y + 1) & 127);
+    int top = v00 * (256 - fx) + v10 * fx, bot = v01 * (256 - fx) + v11 * fx;
+    int v = 64 + ((top * (256 - fy) + bot * fy) >> 16);
+    int cx = x >> 6, cy = y >> 6;
+    for (int dy = -1; dy <= 1; dy++) {
+        for (int dx = -1; dx <= 1; dx++) {
+            int ux = cx + dx, uy = cy + dy;
+            if (ux < 0 || uy < 0) continue;
+            uint64_t h = o_hash4(seed ^ 0xD15Cull, frame, ux, uy);
+            int ox = (ux << 6) + (int)(h & 63), oy = (uy << 6) + (int)((h >> 6) & 63);
+            int r = 6 + (int)((h >> 12) & 31), d = (int)((h >> 20) % 192) - 96;
+            int ddx = x - ox, ddy = y - oy;
+            if (ddx * ddx + ddy * ddy <= r * r) v += d;
+        }
+    }
+    v += (int)(o_hash4(seed ^ 0xA015Eull, frame, x, y) & 15) - 8;
+    return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+int oracle_synth_rows(uint8_t* out, int row0, int rows, int width, int kind, uint64_t seed, int frame) {
+    if (!out || rows < 0 || width <= 0) return -1;
+    for (int r = 0; r < rows; r++)
+        for (int c = 0; c < width; c++) out[(size_t)r * width + c] = o_synth_pixel(kind, seed, frame, c, row0 + r);
+    return 0;
+}

@@ -37,26 +37,48 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = load()
     ctx = cb.Context(local)
-    pipe = sharded.BandPipeline(ctx, a.height, a.width, rank, world, a.sigma, a.lo, a.hi)
-    g = pipe.geo
-    band = torch.empty((g.rows, g.width), dtype=torch.uint8, device="cuda")
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-    check(lib.b200_synth_rows_device(ctx.handle, band.data_ptr(), g.row0, g.rows, g.width, a.kind, 1234, 0))
-    edges = pipe.run(band)
-    torch.cuda.synchronize()
     sizes = [sharded.band_geometry(a.height, a.width, r, world, a.sigma).rows for r in range(world)]
-    parts = [torch.empty((s, a.width), dtype=torch.uint8, device="cuda") for s in sizes] if rank == 0 else None
-    dist.gather(edges, parts, dst=0)
-    ok = True
+    want = None
     if rank == 0:
         from oracle.bindings import Oracle
-        got = torch.cat(parts).cpu().numpy()
         img = cb.synth_host(1, a.height, a.width, kind=a.kind, seed=1234)[0]
         want = Oracle().canny(img, a.sigma, a.lo, a.hi).astype(np.uint8)
-        bad = int((got != want).sum())
-        ok = bad == 0
-        print(json.dumps({"check": "bands_nccl_vs_oracle", "world": world, "height": a.height, "width": a.width, "kind": a.kind,
-                          "edge_pixels": int((got == 255).sum()), "differing_pixels": bad, "ok": ok}))
+    ok = True
+    # the C pipeline over both transports (P2P peer mappings, NCCL), two steps each (the second reuses every buffer and flag), and
+    # the round-1 torch.distributed pipeline as a third opinion
+    for name in ("p2p", "nccl", "torch"):
+        if name == "torch":
+            pipe = sharded.TorchBandPipeline(ctx, a.height, a.width, rank, world, a.sigma, a.lo, a.hi)
+        else:
+            os.environ["B200_BANDS_TRANSPORT"] = name
+            pipe = sharded.BandPipeline(ctx, a.height, a.width, rank, world, a.sigma, a.lo, a.hi)
+        g = pipe.geo
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        band = pipe.band_view()
+        edges = torch.empty((g.rows, g.width), dtype=torch.uint8, device="cuda")
+        for step in range(2):
+            check(lib.b200_synth_rows_device(ctx.handle, band.data_ptr(), g.row0, g.rows, g.width, a.kind, 1234, 0))
+            edges.zero_()
+            pipe.run(None, edges)
+            if name != "torch":
+                pipe.check()
+            torch.cuda.synchronize()
+            parts = [torch.empty((s, a.width), dtype=torch.uint8, device="cuda") for s in sizes] if rank == 0 else None
+            dist.gather(edges, parts, dst=0)
+            if rank == 0:
+                got = torch.cat(parts).cpu().numpy()
+                bad = int((got != want).sum())
+                ok = ok and bad == 0
+                print(json.dumps({"check": "bands_vs_oracle", "pipeline": name, "transport": getattr(pipe, "transport", None), "step": step,
+                                  "world": world, "height": a.height, "width": a.width, "kind": a.kind,
+                                  "edge_pixels": int((got == 255).sum()), "differing_pixels": bad, "ok": bad == 0}))
+        if name != "torch":
+            pipe.close()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    ok = bool(flag.item())
+    if rank == 0:
+        print(json.dumps({"check": "bands_all", "ok": ok}))
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

@@ -11,11 +11,13 @@ from canny_edge_b200 import sharded
 pytestmark = pytest.mark.gpu
 
 
-def check(img, bands, sigma, lo, hi, oracle):
-    got = sharded.canny_bands_virtual(img, bands, sigma, lo, hi)
-    want = oracle.canny(img, sigma, lo, hi).astype(np.uint8)
+def check(img, bands, sigma, lo, hi, oracle, steps=1, want=None):
+    got = sharded.canny_bands_virtual(img, bands, sigma, lo, hi, steps=steps)
+    if want is None:
+        want = oracle.canny(img, sigma, lo, hi).astype(np.uint8)
     bad = np.argwhere(got != want)
     assert bad.size == 0, f"{img.shape} bands={bands} sigma={sigma} {lo}/{hi}: {len(bad)} px differ, first {bad[0].tolist()}"
+    return want
 
 
 @pytest.mark.parametrize("bands", [1, 2, 3, 8])
@@ -54,7 +56,30 @@ def test_bands_quirk_pixel_band_zero(oracle):
 
 def test_bands_4k_image(oracle):
     img = cb.synth_host(1, 2160, 3840, kind=0, seed=1234)[0]
-    check(img, 8, 1.4, 20, 60, oracle)
+    want = check(img, 8, 1.4, 20, 60, oracle, steps=3)   # three steps: both parities of the record buffers, every flag reused
+    check(img, 5, 1.4, 20, 60, oracle, want=want)        # uneven bands (432 rows each, not a multiple of the slab)
+
+
+def test_bands_torch_pipeline_agrees(oracle):
+    """The round-1 pipeline (exchanges in Python around b200_band_front / _boundary_export / _finalize) and the C handle give the
+    same map."""
+    img = cb.synth_host(1, 300, 333, kind=1, seed=21)[0]
+    want = oracle.canny(img, 1.4, 20, 60).astype(np.uint8)
+    assert (sharded.canny_bands_virtual_torch(img, 4, 1.4, 20, 60) == want).all()
+    assert (sharded.canny_bands_virtual(img, 4, 1.4, 20, 60) == want).all()
+
+
+def test_bands_large_image_sigma5_and_gigapixel_class(oracle):
+    """Full-size configs inside the driver-run suite: BASELINE configs[3] (8192 x 8192, sigma = 5: 31 taps, 17-row halos) whole and
+    in 8 bands, and a 32768-wide band case of configs[4]'s geometry (32768 x 1024 in 8 bands of 128 rows)."""
+    img = cb.synth_host(1, 8192, 8192, kind=0, seed=1234)[0]
+    want = oracle.canny(img, 5.0, 20, 60).astype(np.uint8)      # ~13 s on one host core
+    got = cb.cuda_canny(img, 5.0, 20, 60).astype(np.uint8)
+    assert int((got != want).sum()) == 0
+    check(img, 8, 5.0, 20, 60, oracle, want=want)
+    del img, want, got
+    wide = cb.synth_host(1, 1024, 32768, kind=0, seed=99)[0]
+    check(wide, 8, 1.4, 20, 60, oracle)
 
 
 def test_bands_over_nccl_two_gpus():
@@ -71,4 +96,4 @@ def test_bands_over_nccl_two_gpus():
            "--master-port", "29533", str(script), "--height", "2048", "--width", "2048", "--kind", "1"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert '"ok": true' in r.stdout
+    assert '"check": "bands_all", "ok": true' in r.stdout

@@ -189,3 +189,14 @@ def test_oracle_equals_reference_1080p(oracle, ref):
     import canny_edge_b200 as cb
     img = cb.synth_host(1, 1080, 1920, kind=0, seed=1234)[0]
     assert (oracle.canny(img, 1.4, 20, 60) == ref.canny(img, 1.4, 20, 60)).all()
+
+
+def test_oracle_workload_generator_matches_product_generator():
+    """bench.py's CPU legs build their frames with oracle_synth_rows (no product code loaded); the GPU arm with the library's
+    generator.  Both must be the same bytes."""
+    import canny_edge_b200 as cb
+    from oracle.bindings import synth_frames
+    for kind in (0, 1, 2):
+        a = cb.synth_host(2, 70, 300, kind=kind, seed=1234, first_frame=5)
+        b = synth_frames(2, 70, 300, kind=kind, seed=1234, first_frame=5, threads=2)
+        assert (a == b).all(), kind

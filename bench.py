@@ -45,7 +45,7 @@ KINDS = ["shapes", "noise", "const"]
 # Edge count and position-dependent checksum (b200_hash_edges_device) of the Canny map of the 32768 x 32768 "shapes" image (seed
 # 1234, frame 0, sigma 1.4, 20/60).  tests/scripts/config_matrix.py compares the one-GPU map of exactly this image with the compiled
 # reference (oracle/_ref, 147 s on one host thread) pixel by pixel and prints the same two numbers (profiles/r02_config_matrix.json).
-BANDS_EXPECT = {(32768, 32768, 0): None}
+BANDS_EXPECT = {(32768, 32768, 0): (16447230, "dbeef0da0fa5c89a")}
 
 
 def parse():

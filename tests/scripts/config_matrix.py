@@ -64,9 +64,19 @@ def gpu_time(ctx, d_in, d_out, sigma, reps):
     return e0.elapsed_time(e1) / reps
 
 
+def mix64_np(x):
+    """splitmix64 finaliser on a uint64 array (canny_math.h::mix64), wrapping arithmetic."""
+    with np.errstate(over="ignore"):
+        x = x + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return x ^ (x >> np.uint64(31))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-c5-ref", action="store_true")
+    ap.add_argument("--only", default="", help="comma-separated config name prefixes (e.g. C4,C5)")
     ap.add_argument("--out", default="gpurun_out/config_matrix.json")
     a = ap.parse_args()
 
@@ -80,7 +90,10 @@ def main():
     tile = torch.from_numpy(np.fromfile(ROOT / "tests" / "golden" / "test_gray_256x256.u8", dtype=np.uint8).reshape(256, 256)).cuda()
 
     rows = []
+    only = tuple(s for s in a.only.split(",") if s)
     for name, n, h, w, sigma, n_ref in CONFIGS:
+        if only and not name.startswith(only):
+            continue
         for kname, kind in KINDS.items():
             d_in = make_input(lib, ctx, kind, n, h, w, tile)
             d_out = torch.empty_like(d_in)
@@ -100,6 +113,16 @@ def main():
                     e = ref.canny(h_in[f], sigma, LO, HI)
                     secs += ref.last_seconds
                     diff += int(np.count_nonzero((e != 0) != (h_out[f] != 0)))
+                    if name.startswith("C5"):
+                        # edge count + position-dependent checksum of the REFERENCE's map, computed on the host: the pair bench.py
+                        # expects from the row-band run at every GPU count (BANDS_EXPECT) is anchored here
+                        idx = np.flatnonzero(e.ravel() == 255).astype(np.uint64)
+                        row["ref_edge_pixels"] = int(idx.size)
+                        row["ref_checksum"] = f"{int(mix64_np(idx).sum(dtype=np.uint64)):016x}"
+                        hs = C.c_ulonglong()
+                        check(lib.b200_hash_edges_device(ctx.handle, d_out.data_ptr(), d_out.numel(), 0, C.byref(hs)))
+                        row["gpu_edge_pixels"], row["gpu_checksum"] = int(edges.value), f"{hs.value:016x}"
+                        del idx
                     del e
                 row.update({"ref_frames": n_ref, "ref_1thread_s": round(secs, 4), "ref_1thread_Mpix_s": round(n_ref * h * w / secs / 1e6, 2),
                             "differing_px": diff, "speedup_vs_1thread": round((px / ms / 1e3) / (n_ref * h * w / secs / 1e6), 1)})

@@ -37,6 +37,10 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = load()
     ctx = cb.Context(local)
+    # an explicit stream: torch's DEFAULT stream is handle 0, which b200_ctx_set_stream takes as "use the context's private stream" —
+    # the context's kernels would then not be ordered with torch's own work (zero_, NCCL) on the default stream
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     sizes = [sharded.band_geometry(a.height, a.width, r, world, a.sigma).rows for r in range(world)]
     want = None
     if rank == 0:

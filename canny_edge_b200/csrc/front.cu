@@ -548,7 +548,8 @@ static int launch_front_v1(b200_ctx* ctx, cudaStream_t st, const FrontParams& p_
 }
 
 // Dispatcher: the lean kernel (front2.cu) for the hot configuration — compile-time radius, no spill planes,
-// ordinary sigma; front_kernel above for everything else.  B200_CANNY_FRONT=1 forces the first kernel (A/B runs).
+// ordinary sigma: front3.cu's kernel (front2.cu's with B200_CANNY_FRONT=2); front_kernel above for everything else
+// (B200_CANNY_FRONT=1 forces it: A/B runs).
 int launch_front(b200_ctx* ctx, cudaStream_t st, const FrontParams& p_in, bool* sparse_out) {
     FrontParams p = p_in;
     if (sparse_out) *sparse_out = false;
@@ -558,7 +559,8 @@ int launch_front(b200_ctx* ctx, cudaStream_t st, const FrontParams& p_in, bool* 
         set_error("gaussian radius %d outside [1,%d]", radius, B200_MAX_RADIUS);
         return B200_ERR_UNSUPPORTED;
     }
-    static const bool force_v1 = [] { const char* e = getenv("B200_CANNY_FRONT"); return e && e[0] == '1'; }();
+    static const int force = [] { const char* e = getenv("B200_CANNY_FRONT"); return e ? atoi(e) : 0; }();
+    const bool force_v1 = force == 1;
     const bool spill = p.blur || p.mag || p.ang || p.nms;
     if (!force_v1 && !spill && !ctx->gauss.tiny && front2_supports(radius)) {
         // the sparse hand-over lists KEPT pixels; with minVal <= 0 suppressed pixels are candidates too (src/utils.cpp:328), so the
@@ -567,6 +569,7 @@ int launch_front(b200_ctx* ctx, cudaStream_t st, const FrontParams& p_in, bool* 
                             (long long)p.n_frames * p.out_frame_stride < (1LL << 31);
         if (!sparse) { p.parent = nullptr; p.kept_list = nullptr; p.kept_count = nullptr; }
         if (sparse_out) *sparse_out = sparse;
+        if (force != 2 && front3_supports(radius)) return launch_front3(ctx, st, p);
         return launch_front2(ctx, st, p);
     }
     return launch_front_v1(ctx, st, p);

@@ -218,6 +218,9 @@ int make_input_tensor_map(const FrontParams& p, int box_cols, int box_rows, CUte
 // front2.cu
 bool front2_supports(int radius);
 int launch_front2(b200_ctx* ctx, cudaStream_t st, const FrontParams& p);
+// front3.cu (packed-FP32 blur, half-precision Sobel; the default for the radii it is built for)
+bool front3_supports(int radius);
+int launch_front3(b200_ctx* ctx, cudaStream_t st, const FrontParams& p);
 // selftest.cu
 int check_div_mode_device(b200_ctx* ctx, float b, float y, float* c, int* mode);
 // hysteresis.cu

@@ -41,9 +41,9 @@ constexpr int kVuPitch = 132;    // int32 words; lane 31 of the last phase reads
 // outputs per thread: SLAB/2 in the row pass, SLAB/2 VU rows = SLAB/2 + 2 blurred rows in the column pass
 
 __host__ __device__ constexpr int in_pitch_for(int radius) {
-    // bytes per staged input row: up to 15 leading bytes (the TMA box starts on a 16 B boundary of the image
-    // row), 128 + 2R needed ones; a multiple of 16 (TMA) and an ODD multiple so lane = row 128-bit loads spread
-    // over 8 distinct bank groups
+    // bytes per staged input row: up to 15 leading bytes (the TMA box must start on a 16 B boundary of the image row: a tile
+    // coordinate that is not a multiple of 16 bytes traps — tools/probes/tma_probe.cu), 128 + 2R needed ones; a multiple of 16
+    // (TMA) and an ODD multiple so lane = row 128-bit loads spread over 8 distinct bank groups
     int k = (15 + kTC + 2 * radius + 15) / 16;
     if ((k & 1) == 0) k += 1;
     return 16 * k;
@@ -305,146 +305,169 @@ front3_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
         }
         const unsigned char* slab = s_in + (k % kInBufs) * slab_bytes;
 
-        // ===================== phase 1: row blur, u8 -> f32 (src/utils.cpp:37-49), two rows per thread =====================
-        // thread = (slab rows lane and lane + 32, 16 columns starting at 16*warp); temp buffer row T0 + slab row.
-        // A pair = {row lane, row lane+32} at one column.
+        // ===================== phase 1: row blur, u8 -> f32 (src/utils.cpp:37-49), two column segments per thread =====================
+        // thread = (slab row 32*(warp>>2) + lane, columns 16*sp .. +15 AND 64 + 16*sp .. +15, sp = warp & 3).  A pair = {column c,
+        // column c + 64} of the row, and that is also how the temp buffer keeps a line: float 2c <-> column c, float 2c+1 <-> column
+        // c + 64 (c < 64), so two outputs are one 128-bit store and the column pass loads a pair as one 64-bit word.
         {
-            const int seg = warp;                                // 8 segments of 16 columns
-            // needed bytes of a line: [16*seg + lead, 16*seg + lead + 16 + 2R).  lead = 4*dq + DR with DR a compile-time constant
+            const int srow = 32 * (warp >> 2) + lane;
+            const int sp = warp & 3;
+            // needed bytes of a segment: [16*seg + lead, 16*seg + lead + 16 + 2R).  lead = 4*dq + DR with DR a compile-time constant
             // (x0 is a multiple of 4) and dq uniform over the CTA: load aligned 128-bit vectors, shift by dq WORDS with a uniform
             // switch, pick bytes with static selectors.
             constexpr int DR = (((-2 - R) % 4) + 4) % 4;
             constexpr int KW = (DR + kRunRow + 2 * R + 3) / 4;   // words holding the needed bytes
             constexpr int NV = (KW + 3 + 3) / 4;                 // vectors covering KW + 3 words
             static_assert((kTC - kRunRow) + 16 * NV <= in_pitch, "row pass would read past the staged line");
-            uint32_t wa[NV * 4], wb[NV * 4];
-            const uint4* src_a = reinterpret_cast<const uint4*>(slab + lane * in_pitch + seg * kRunRow);
-            const uint4* src_b = reinterpret_cast<const uint4*>(slab + (lane + 32) * in_pitch + seg * kRunRow);
+            uint32_t va[NV * 4], vb[NV * 4];
+            const uint4* src_a = reinterpret_cast<const uint4*>(slab + srow * in_pitch + sp * kRunRow);
+            const uint4* src_b = reinterpret_cast<const uint4*>(slab + srow * in_pitch + sp * kRunRow + kTC / 2);
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
                 const uint4 ta = src_a[v], tb = src_b[v];
-                wa[4 * v + 0] = ta.x; wa[4 * v + 1] = ta.y; wa[4 * v + 2] = ta.z; wa[4 * v + 3] = ta.w;
-                wb[4 * v + 0] = tb.x; wb[4 * v + 1] = tb.y; wb[4 * v + 2] = tb.z; wb[4 * v + 3] = tb.w;
+                va[4 * v + 0] = ta.x; va[4 * v + 1] = ta.y; va[4 * v + 2] = ta.z; va[4 * v + 3] = ta.w;
+                vb[4 * v + 0] = tb.x; vb[4 * v + 1] = tb.y; vb[4 * v + 2] = tb.z; vb[4 * v + 3] = tb.w;
             }
-            uint32_t a2[KW], b2[KW];
+            uint32_t wa[KW], wb[KW];
             switch (lead >> 2) {
                 case 0:
 #pragma unroll
-                    for (int q = 0; q < KW; ++q) { a2[q] = wa[q]; b2[q] = wb[q]; }
+                    for (int q = 0; q < KW; ++q) { wa[q] = va[q]; wb[q] = vb[q]; }
                     break;
                 case 1:
 #pragma unroll
-                    for (int q = 0; q < KW; ++q) { a2[q] = wa[q + 1]; b2[q] = wb[q + 1]; }
+                    for (int q = 0; q < KW; ++q) { wa[q] = va[q + 1]; wb[q] = vb[q + 1]; }
                     break;
                 case 2:
 #pragma unroll
-                    for (int q = 0; q < KW; ++q) { a2[q] = wa[q + 2]; b2[q] = wb[q + 2]; }
+                    for (int q = 0; q < KW; ++q) { wa[q] = va[q + 2]; wb[q] = vb[q + 2]; }
                     break;
                 default:
 #pragma unroll
-                    for (int q = 0; q < KW; ++q) { a2[q] = wa[q + 3]; b2[q] = wb[q + 3]; }
+                    for (int q = 0; q < KW; ++q) { wa[q] = va[q + 3]; wb[q] = vb[q + 3]; }
                     break;
             }
-            float* trow_a = s_temp + (T0 + lane) * kTempPitch + seg * kRunRow;
-            float* trow_b = trow_a + 32 * kTempPitch;
-            const int gx_first = x0 - 2 + seg * kRunRow;  // image column of output 0
-            u64 grp[4];
-            blur_run2<R, kRunRow>(
-                ws2,
-                [&](int i) {
-                    // {byte, 0, 0, 0x4B} = 2^23 + byte for both rows, then ONE packed subtraction of 2^23
-                    const uint32_t sel = 0x7650 + ((i + DR) & 3);
-                    const uint32_t ba = __byte_perm(a2[(i + DR) >> 2], 0x4B000000u, sel);
-                    const uint32_t bb = __byte_perm(b2[(i + DR) >> 2], 0x4B000000u, sel);
-                    return add2(pack2(__uint_as_float(ba), __uint_as_float(bb)), kNegBias2);
-                },
-                [&](int o, u64 sum) {
-                    grp[o & 3] = sum;
-                    if ((o & 3) == 3) {
-                        // divide by the in-image weight sum (src/utils.cpp:47) and store four outputs per row
-                        float ra[4], rb[4];
-                        if (x_interior) {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) unpack2(div_const2<DIV>(grp[e], ncnt2, rcp2, divc2), ra[e], rb[e]);
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int gx = gx_first + (o - 3) + e;
-                                unpack2(grp[e], ra[e], rb[e]);
-                                if (gx < 0 || gx >= W) { ra[e] = 0.f; rb[e] = 0.f; continue; }
-                                const int ta = max(0, R - gx), tb = max(0, gx + R - (W - 1));
-                                const int ti = ta * (R + 1) + tb;
-                                ra[e] = div_exact(ra[e], s_cnt[ti], s_rcp[ti]);
-                                rb[e] = div_exact(rb[e], s_cnt[ti], s_rcp[ti]);
-                            }
-                        }
-                        *reinterpret_cast<float4*>(trow_a + (o - 3)) = make_float4(ra[0], ra[1], ra[2], ra[3]);
-                        *reinterpret_cast<float4*>(trow_b + (o - 3)) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+            float* trow = s_temp + (T0 + srow) * kTempPitch + 2 * sp * kRunRow;   // interleaved line: output o of the pair at floats 2o, 2o+1
+            int gx_first = x0 - 2 + sp * kRunRow;   // image column of output 0 of the first segment (the second: + 64)
+            asm volatile("" : "+r"(gx_first));      // keeps the border strips' table indices from being hoisted out of the slab loop (registers)
+            auto fetch = [&](int i) {
+                // {byte, 0, 0, 0x4B} = 2^23 + byte for both columns, then ONE packed subtraction of 2^23
+                const uint32_t sel = 0x7650 + ((i + DR) & 3);
+                const uint32_t ba = __byte_perm(wa[(i + DR) >> 2], 0x4B000000u, sel);
+                const uint32_t bb = __byte_perm(wb[(i + DR) >> 2], 0x4B000000u, sel);
+                return add2(pack2(__uint_as_float(ba), __uint_as_float(bb)), kNegBias2);
+            };
+            u64 prev = 0;
+            // two straight-line copies: the WARP-uniform choice of the division is made once, not inside the unrolled run.  Only the
+            // warps whose two segments touch the image border (1 in 4 of a border strip's warps) take the per-column weight sums.
+            const bool seg_interior = x_interior || ((gx_first - R >= 0) && (gx_first + kTC / 2 + kRunRow - 1 + R <= W - 1));
+            if (seg_interior) {
+                blur_run2<R, kRunRow>(ws2, fetch, [&](int o, u64 sum) {
+                    const u64 q = div_const2<DIV>(sum, ncnt2, rcp2, divc2);      // divide by the weight sum (src/utils.cpp:47)
+                    if (o & 1) {
+                        float a0, a1, b0, b1;
+                        unpack2(prev, a0, a1);
+                        unpack2(q, b0, b1);
+                        *reinterpret_cast<float4*>(trow + 2 * (o - 1)) = make_float4(a0, a1, b0, b1);
                     }
+                    prev = q;
                 });
+            } else {
+                blur_run2<R, kRunRow>(ws2, fetch, [&](int o, u64 sum) {
+                    // strips at the left / right image border: per-column in-image weight sums
+                    float r01[2];
+                    unpack2(sum, r01[0], r01[1]);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int gx = gx_first + o + e * (kTC / 2);
+                        if (gx < 0 || gx >= W) { r01[e] = 0.f; continue; }
+                        const int ta = max(0, R - gx), tb = max(0, gx + R - (W - 1));
+                        const int ti = ta * (R + 1) + tb;
+                        r01[e] = div_exact(r01[e], s_cnt[ti], s_rcp[ti]);
+                    }
+                    const u64 q = pack2(r01[0], r01[1]);
+                    if (o & 1) {
+                        float a0, a1;
+                        unpack2(prev, a0, a1);
+                        *reinterpret_cast<float4*>(trow + 2 * (o - 1)) = make_float4(a0, a1, r01[0], r01[1]);
+                    }
+                    prev = q;
+                });
+            }
         }
         if (sparse) flush_pending();
         __syncthreads();  // (A) this slab's temp lines are complete; staged buffer k&1 is free again
         if (USE_TMA && k + kInBufs < n_slabs) issue_slab(k + kInBufs);
 
         // ===================== phase 2: column blur f32 -> int (src/utils.cpp:52-64) + vertical half of Sobel, two columns per thread ====
-        // thread = (columns 2*(tid&63), +1; row group tid>>6).  Blurred rows Bg(o) = I_k - R - 2 + 16*group + o, o = 0..17, from temp
-        // buffer rows 16*group + o .. + 2R; VU rows Bg(1..16) go to VU buffer rows 2 + 16*group + (o-2).  A pair = the two columns.
+        // thread = (columns c = tid&63 and c + 64; row group tid>>6).  Blurred rows Bg(o) = I_k - R - 2 + 16*group + o, o = 0..17, from temp
+        // buffer rows 16*group + o .. + 2R; VU rows Bg(1..16) go to VU buffer rows 2 + 16*group + (o-2).  A pair = the two columns, one
+        // 64-bit word of the interleaved temp line.
         {
-            const int c = 2 * (tid & 63);
+            const int c = tid & 63;
             const int group = tid >> 6;
-            const float* tcol = s_temp + (kRunV * group) * kTempPitch + c;
+            const float* tcol = s_temp + (kRunV * group) * kTempPitch + 2 * c;
             uint32_t* vcol = reinterpret_cast<uint32_t*>(s_vu) + (2 + kRunV * group) * kVuPitch + c;
             const int bg0 = I_k - R - 2 + kRunV * group;  // global row of blurred output 0
             // interior run: every blurred row has all 2R+1 taps inside the image, and every VU row has both vertical neighbours
             const bool y_interior = (bg0 - R >= 0) && (bg0 + kRunCol - 1 + R <= H - 1);
-            u64 b0 = 0, b1 = 0;  // blurred values (exact integers in fp32) of rows o-2, o-1, both columns
-            blur_run2<R, kRunCol>(
-                ws2, [&](int i) { return *reinterpret_cast<const u64*>(tcol + i * kTempPitch); },
-                [&](int o, u64 sum) {
-                    u64 b2;
-                    if (y_interior) {
+            if (y_interior) {
+                u64 b0 = 0, b1 = 0;  // blurred values (exact integers in fp32) of rows o-2, o-1, both columns
+                blur_run2<R, kRunCol>(
+                    ws2, [&](int i) { return *reinterpret_cast<const u64*>(tcol + i * kTempPitch); },
+                    [&](int o, u64 sum) {
                         // (short)(sum / count) of src/utils.cpp:62: adding 2^23 toward zero leaves 2^23 + trunc(q); subtracting it
                         // again (exact) gives trunc(q) as a float
-                        b2 = add2(add2_rz(div_const2<DIV>(sum, ncnt2, rcp2, divc2), kBias2), kNegBias2);
+                        const u64 b2 = add2(add2_rz(div_const2<DIV>(sum, ncnt2, rcp2, divc2), kBias2), kNegBias2);
                         if (o >= 2) {
                             float v0, v1, u0, u1;
                             unpack2(add2(fma2(b1, kTwo2, b0), b2), v0, v1);   // B[r-1] + 2 B[r] + B[r+1]
                             unpack2(fma2(b0, kNegOne2, b2), u0, u1);          // B[r+1] - B[r-1]
-                            *reinterpret_cast<uint2*>(vcol + (o - 2) * kVuPitch) = make_uint2(pack_half2(v0, u0), pack_half2(v1, u1));
+                            vcol[(o - 2) * kVuPitch] = pack_half2(v0, u0);
+                            vcol[(o - 2) * kVuPitch + kTC / 2] = pack_half2(v1, u1);
                         }
-                    } else {
-                        // border run: per-row counts, rows outside the image, replicate / drop rules of src/utils.cpp:117-184
-                        const int gy = bg0 + o;
-                        float s01[2], pm[2], pc[2], cur[2] = {0.f, 0.f};
-                        unpack2(sum, s01[0], s01[1]);
-                        unpack2(b0, pm[0], pm[1]);
-                        unpack2(b1, pc[0], pc[1]);
-                        if (gy >= 0 && gy < H) {
-                            const int ta = max(0, R - gy), tb = max(0, gy + R - (H - 1));
-                            const int ti = ta * (R + 1) + tb;
+                        b0 = b1; b1 = b2;
+                    });
+            } else {
+                // border run (first / last slabs of the image only): a compact loop — direct 2R+1-tap sums per output, per-row counts,
+                // rows outside the image, replicate / drop rules of src/utils.cpp:117-184.  Same products and sums, same order.
+                float pm[2] = {0.f, 0.f}, pc[2] = {0.f, 0.f};
+#pragma unroll 1
+                for (int o = 0; o < kRunCol; ++o) {
+                    u64 sum = 0;
 #pragma unroll
-                            for (int e = 0; e < 2; ++e)
-                                cur[e] = __fsub_rn(__fadd_rz(div_exact(s01[e], s_cnt[ti], s_rcp[ti]), 8388608.0f), 8388608.0f);
-                        }
-                        b2 = pack2(cur[0], cur[1]);
-                        if (o >= 2) {
-                            const int r = gy - 1;  // the VU row: blurred rows r-1 (pm), r (pc), r+1 (cur)
-                            uint32_t word[2] = {0u, 0u};
-                            if (r >= 0 && r < H) {
-#pragma unroll
-                                for (int e = 0; e < 2; ++e) {
-                                    const float up = (r > 0) ? pm[e] : pc[e], dn = (r < H - 1) ? cur[e] : pc[e];        // vertical replicate (gy term)
-                                    const float u = dn - up;
-                                    const float v = 2.f * pc[e] + ((r > 0) ? pm[e] : 0.f) + ((r < H - 1) ? cur[e] : 0.f);  // vertical drop (gx term)
-                                    word[e] = pack_half2(v, u);
-                                }
-                            }
-                            *reinterpret_cast<uint2*>(vcol + (o - 2) * kVuPitch) = make_uint2(word[0], word[1]);
-                        }
+                    for (int t = 0; t <= 2 * R; ++t) {
+                        const u64 q = mul2_ftz(*reinterpret_cast<const u64*>(tcol + (o + t) * kTempPitch), ws2[t < R ? R - t : t - R]);
+                        sum = (t == 0) ? q : add2(sum, q);
                     }
-                    b0 = b1; b1 = b2;
-                });
+                    const int gy = bg0 + o;
+                    float s01[2], cur[2] = {0.f, 0.f};
+                    unpack2(sum, s01[0], s01[1]);
+                    if (gy >= 0 && gy < H) {
+                        const int ta = max(0, R - gy), tb = max(0, gy + R - (H - 1));
+                        const int ti = ta * (R + 1) + tb;
+#pragma unroll
+                        for (int e = 0; e < 2; ++e)
+                            cur[e] = __fsub_rn(__fadd_rz(div_exact(s01[e], s_cnt[ti], s_rcp[ti]), 8388608.0f), 8388608.0f);
+                    }
+                    if (o >= 2) {
+                        const int r = gy - 1;  // the VU row: blurred rows r-1 (pm), r (pc), r+1 (cur)
+                        uint32_t word[2] = {0u, 0u};
+                        if (r >= 0 && r < H) {
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const float up = (r > 0) ? pm[e] : pc[e], dn = (r < H - 1) ? cur[e] : pc[e];        // vertical replicate (gy term)
+                                const float u = dn - up;
+                                const float v = 2.f * pc[e] + ((r > 0) ? pm[e] : 0.f) + ((r < H - 1) ? cur[e] : 0.f);  // vertical drop (gx term)
+                                word[e] = pack_half2(v, u);
+                            }
+                        }
+                        vcol[(o - 2) * kVuPitch] = word[0];
+                        vcol[(o - 2) * kVuPitch + kTC / 2] = word[1];
+                    }
+                    pm[0] = pc[0]; pm[1] = pc[1]; pc[0] = cur[0]; pc[1] = cur[1];
+                }
+            }
         }
         __syncthreads();  // (B) VU rows 2..65 complete; every read of the temp buffer is done
 
@@ -533,7 +556,15 @@ front3_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
                     my_count += n_lo + __popc(vote_hi);
                 };
                 // every class word starts out as "suppressed"; phase 3b overwrites the bytes of surviving pixels
-                if (__all_sync(0xffffffffu, word_ok || lane >= kTW / 4)) {
+                if (cq_lo == 1 && cq_hi == kSlab && ((W & 3) == 0)) {
+                    // the common slab (all 64 class rows, image width a multiple of 4): the warp's eight rows unrolled, every address an
+                    // immediate offset from the first row's (word_ok is false for the columns past a ragged right edge)
+#pragma unroll
+                    for (int i = 0; i < kSlab / 8; ++i) {
+                        class_row(vrow + 8 * i * kVuPitch, nrow + 8 * i * kNpPitch, ent + ((8 * i) << 6));
+                        if (word_ok) *reinterpret_cast<uint32_t*>(o + i * o_step) = zero_word;
+                    }
+                } else if (__all_sync(0xffffffffu, word_ok || lane >= kTW / 4)) {
                     for (; q <= cq_hi; q += 8, vrow += 8 * kVuPitch, nrow += 8 * kNpPitch, o += o_step, ent += 8 << 6) {
                         class_row(vrow, nrow, ent);
                         if (lane < kTW / 4) *reinterpret_cast<uint32_t*>(o) = zero_word;

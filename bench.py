@@ -225,6 +225,10 @@ class Env:
             raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU path)")
         self.torch, self.dist, self.cb, self.check = torch, dist, cb, check
         self.rank, self.world, self.local = rank, world, local_rank
+        # host placement first: this thread, the library's host pool and the pinned buffers (first touch) go to the GPU's NUMA node
+        node = C.c_int(-1)
+        load().b200_host_bind_numa(local_rank, C.byref(node))
+        self.numa_node = node.value
         torch.cuda.set_device(local_rank)
         if world > 1:
             dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -441,7 +445,14 @@ def run_b200(a, rank, world, local_rank):
                     "h2d_bytes_per_step": (b1h.value - b0h.value) // a.e2e_steps, "d2h_bytes_per_step": (b1d.value - b0d.value) // a.e2e_steps,
                     "steps": a.e2e_steps, "ms_per_step": round(ems / a.e2e_steps, 3)}
 
+        # what the host memory system gives this rank: one pass of the library's own multi-threaded copy over the input batch
+        t0 = time.perf_counter()
+        h_out.copy_(h_in)
+        host_copy_gbs = 2 * px_e / (time.perf_counter() - t0) / 1e9
         e2e = e2e_leg(lambda: check(lib.b200_canny_batch_host(ctx.handle, h_in.data_ptr(), ne, h, w, C.c_float(SIGMA), LO, HI, h_out.data_ptr())))
+        e2e["host"] = {"numa_node_bound": env.numa_node, "pinned_copy_gbs_one_thread": round(host_copy_gbs, 1), "cpus_visible": len(os.sched_getaffinity(0)),
+                       "note": "every rank's frames and maps cross the same host memory system and PCIe root complexes: the e2e figure stops scaling "
+                               "where they saturate; the packed form moves 1/8 of the map bytes through host DRAM and no expansion pass"}
         e2e["api"] = ("b200_canny_batch_host (pinned host u8 frames in -> pinned host u8 0/255 edge maps out; the maps cross PCIe bit-packed and "
                       "are expanded by the library's host threads inside the timed call)")
         e2e["matches_device_run"] = bool((h_out.view(-1)[:: 4099] == d_out[:ne].cpu().view(-1)[:: 4099]).all()) if px_e < (1 << 33) else None

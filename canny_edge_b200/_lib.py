@@ -41,6 +41,8 @@ SIGNATURES = {
     "b200_ctx_set_chunk_frames": (C.c_int, [_ctx, C.c_int]),
     "b200_ctx_kernel_launches": (C.c_longlong, [_ctx]),
     "b200_ctx_transfer_bytes": (C.c_int, [_ctx, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
+    "b200_ctx_front_kernel_stats": (C.c_int, [_ctx, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    "b200_host_bind_numa": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
     "b200_gaussian_window": (C.c_int, [C.c_float]),
     "b200_gaussian_kernel": (C.c_int, [C.c_float, _f32p, C.POINTER(C.c_int)]),
     "b200_direction_host": (C.c_int, [C.c_int, C.c_int]),

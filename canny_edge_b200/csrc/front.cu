@@ -569,9 +569,18 @@ int launch_front(b200_ctx* ctx, cudaStream_t st, const FrontParams& p_in, bool* 
                             (long long)p.n_frames * p.out_frame_stride < (1LL << 31);
         if (!sparse) { p.parent = nullptr; p.kept_list = nullptr; p.kept_count = nullptr; }
         if (sparse_out) *sparse_out = sparse;
+        ctx->front_fast++;
         if (force != 2 && front3_supports(radius)) return launch_front3(ctx, st, p);
         return launch_front2(ctx, st, p);
     }
+    // The generic kernel is 3-4x slower than the lean ones.  It is the right one for spill planes (stage API, `steps`); for a plain
+    // map it means sigma's half-window is not in the compiled set {2,3,5,6,9,15}: say so once per context instead of silently
+    // running at a quarter of the speed (b200_ctx_front_kernel_stats counts both kinds).
+    if (!spill && !force_v1 && ctx->front_generic == 0 && getenv("B200_CANNY_QUIET") == nullptr)
+        fprintf(stderr, "libcanny_b200: gaussian half-window %d (sigma %g) has no specialised front kernel (built: 2, 3, 5, 6, 9, 15)%s; "
+                        "using the generic kernel (about 4x slower). Set B200_CANNY_QUIET=1 to silence.\n",
+                radius, (double)ctx->gauss.sigma, ctx->gauss.tiny ? " and its weights reach the subnormal range" : "");
+    ctx->front_generic++;
     return launch_front_v1(ctx, st, p);
 }
 

@@ -173,6 +173,7 @@ struct b200_ctx {
     cb::Workspace ws_band_aux;            // boundary roots of the resident band + the cross-band forest
     int chunk_frames = 0;
     long long launches = 0;
+    long long front_fast = 0, front_generic = 0;   // front-kernel launches on the lean kernels (front3 / front2) and on front.cu's generic one
     unsigned long long h2d_bytes = 0, d2h_bytes = 0;  // PCIe bytes moved by b200_canny_batch_host so far
     cb::Profiler prof;
     // band state (row-band sharding)

@@ -69,6 +69,16 @@ long long b200_ctx_kernel_launches(const b200_ctx* ctx);
  * maps of jobs >= 8 Mpix come back bit-packed, 1 bit per pixel, and are expanded to 0 / 255 bytes on the host). */
 int b200_ctx_transfer_bytes(const b200_ctx* ctx, unsigned long long* h2d_bytes, unsigned long long* d2h_bytes);
 
+/* Front-kernel launches so far on this context: on the specialised kernels (Gaussian half-window 2, 3, 5, 6, 9 or 15 — sigma 1.4
+ * is 5, sigma 5 is 15 — and no per-stage planes requested) and on the generic one (any half-window up to B200_MAX_RADIUS, spill
+ * planes; about 4x slower).  The first plain-map launch that falls back also prints one line on stderr (B200_CANNY_QUIET=1
+ * silences it). */
+int b200_ctx_front_kernel_stats(const b200_ctx* ctx, long long* fast_launches, long long* generic_launches);
+/* Pins the calling thread — and the threads and first-touch pinned allocations it makes afterwards — to the CPUs of the NUMA node
+ * `device` is attached to (sysfs); *node_out = that node, or -1 when nothing was changed (single-node host, no permission).  Call
+ * it before b200_ctx_create / before allocating pinned buffers in a one-process-per-GPU deployment. */
+int b200_host_bind_numa(int device, int* node_out);
+
 /* In every function below ctx may be NULL: a lazily created process-wide context on the current
  * CUDA device is used (what the reference-signature C++ shims in canny_b200_compat.hpp do). */
 

@@ -345,14 +345,24 @@ ccl_sparse_resolve_kernel(const HystParams p) {
     }
 }
 
-// the list length lives on the device: a fixed grid (every SM full once) strides over it
-static int sparse_grid(const b200_ctx* ctx) { return 8 * (ctx->sm_count > 0 ? ctx->sm_count : 148); }
+// The list length lives on the device, so the grid is sized from the launch's pixel count: one 256-thread block per 16 Ki pixels
+// (1.5 % of them weak = one entry per thread), at least 32 blocks, at most every SM full once; the kernels stride over the list, so
+// any grid is correct.  A small frame must not pay for 1184 blocks: every block of the link kernel takes a ticket on ONE counter
+// (the last one applies the reference's one-way link), and 1184 serialised atomics alone are ~12 us of a 1080p frame's 45.
+static int sparse_grid(const b200_ctx* ctx, const HystParams& p) {
+    const long long px = (long long)p.n_frames * p.frame_stride;
+    const long long cap = 8LL * (ctx->sm_count > 0 ? ctx->sm_count : 148);
+    long long b = px / 16384;
+    if (b < 32) b = 32;
+    if (b > cap) b = cap;
+    return (int)b;
+}
 
 int launch_ccl_label(b200_ctx* ctx, cudaStream_t st, const HystParams& p_in) {
     HystParams p = p_in;
     if (p.list) {
         ProfScope ps(ctx, st, 1);
-        ccl_sparse_link_kernel<<<sparse_grid(ctx), 256, 0, st>>>(p);
+        ccl_sparse_link_kernel<<<sparse_grid(ctx, p), 256, 0, st>>>(p);
         CB_CUDA(cudaGetLastError());
         ctx->launches++;
         return B200_OK;
@@ -389,7 +399,7 @@ int launch_ccl_resolve(b200_ctx* ctx, cudaStream_t st, const HystParams& p_in) {
     HystParams p = p_in;
     if (p.list) {
         ProfScope ps(ctx, st, 3);
-        ccl_sparse_resolve_kernel<<<sparse_grid(ctx), 256, 0, st>>>(p);
+        ccl_sparse_resolve_kernel<<<sparse_grid(ctx, p), 256, 0, st>>>(p);
         CB_CUDA(cudaGetLastError());
         ctx->launches++;
         return B200_OK;

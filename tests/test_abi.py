@@ -116,3 +116,16 @@ def test_unpack_edges_host_matches_numpy():
                     assert (raw[off + n_px:] == 77).all() and (raw[:off] == 77).all(), "wrote outside the output"
     assert lib.b200_unpack_edges_host(None, 8, None, 1, 1) != 0
     assert lib.b200_unpack_edges_host(bits.ctypes.data, 8, out.ctypes.data, 4, 1) != 0
+
+
+def test_host_bind_numa_is_harmless_without_gpu():
+    """b200_host_bind_numa never fails the caller: without a device it reports an error status and changes nothing."""
+    import ctypes as C
+    import os
+    lib = cb.load()
+    before = os.sched_getaffinity(0)
+    node = C.c_int(7)
+    st = lib.b200_host_bind_numa(0, C.byref(node))
+    assert st in (0, 2)                     # B200_OK on a GPU box, B200_ERR_NO_DEVICE here
+    assert os.sched_getaffinity(0) <= before   # only ever narrowed
+    os.sched_setaffinity(0, before)

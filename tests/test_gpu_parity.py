@@ -506,3 +506,42 @@ def test_pack_edges_device_round_trip(gpu_ctx):
         out = np.empty((h, w), np.int16)
         check(lib.b200_unpack_edges_host(bits.ctypes.data, n_px, out.ctypes.data, 2, 0))
         assert (out == edges).all()
+
+
+def test_packed_batch_host_matches_byte_maps(gpu_ctx, oracle):
+    """b200_canny_batch_host_packed: 1 bit per pixel, every frame starting on a 32-bit word; sizes whose pixel count is and is not a
+    multiple of 32; chunked (several chunks in flight) and single-chunk."""
+    lib = load()
+    for n, h, w in [(5, 64, 96), (3, 33, 47), (4, 130, 250)]:
+        frames = cb.synth_host(n, h, w, kind=1, seed=40 + h)
+        fw = (h * w + 31) // 32
+        bits = np.zeros((n, fw), np.uint32)
+        for chunk in (0, 2):
+            check(lib.b200_ctx_set_chunk_frames(gpu_ctx.handle, chunk))
+            bits[:] = 0xFFFFFFFF
+            check(lib.b200_canny_batch_host_packed(gpu_ctx.handle, frames.ctypes.data, n, h, w, C.c_float(1.4), 20, 60, bits.ctypes.data))
+            for f in range(n):
+                got = np.unpackbits(bits[f].view(np.uint8), bitorder="little")[: h * w].reshape(h, w)
+                want = oracle.canny(frames[f], 1.4, 20, 60) == 255
+                assert (got.astype(bool) == want).all(), (n, h, w, chunk, f)
+        check(lib.b200_ctx_set_chunk_frames(gpu_ctx.handle, 0))
+
+
+def test_front_kernel_stats_and_fallback_is_counted(gpu_ctx, oracle, capfd):
+    """sigma outside the compiled half-windows runs the generic kernel: same results, counted, and announced once on stderr."""
+    lib = load()
+    ctx = cb.Context(0)
+    try:
+        img = cb.synth_host(1, 96, 160, kind=0, seed=3)[0]
+        fast0, gen0 = C.c_longlong(), C.c_longlong()
+        check(lib.b200_ctx_front_kernel_stats(ctx.handle, C.byref(fast0), C.byref(gen0)))
+        assert (cb.cuda_canny(img, 1.4, 20, 60, ctx=ctx) == oracle.canny(img, 1.4, 20, 60)).all()      # half-window 5: specialised
+        assert (cb.cuda_canny(img, 1.2, 20, 60, ctx=ctx) == oracle.canny(img, 1.2, 20, 60)).all()      # half-window 4: generic
+        assert (cb.cuda_canny(img, 2.5, 20, 60, ctx=ctx) == oracle.canny(img, 2.5, 20, 60)).all()      # half-window 8: generic
+        fast1, gen1 = C.c_longlong(), C.c_longlong()
+        check(lib.b200_ctx_front_kernel_stats(ctx.handle, C.byref(fast1), C.byref(gen1)))
+        assert fast1.value - fast0.value == 1 and gen1.value - gen0.value == 2
+        err = capfd.readouterr().err
+        assert err.count("no specialised front kernel") == 1
+    finally:
+        ctx.close()

@@ -36,3 +36,8 @@ print("UTMALDG (TMA tensor load):", ops["UTMALDG"], " SYNCS (mbarrier):", ops["S
       ops["FFMA2"] + ops["FMUL2"] + ops["FADD2"])
 print("FMUL:", ops["FMUL"], " FADD:", ops["FADD"], " FFMA:", ops["FFMA"],
       "(FFMA only inside the exact division: 2 per quotient in the 3-step form, 4 in the 5-step form)")
+if ops["FMUL2"] or ops["FADD2"]:
+    ftz = sum(1 for line in keep if "FMUL2.FTZ" in line)
+    print("packed blur: FMUL2.FTZ", ftz, "of", ops["FMUL2"], "FMUL2;  FADD2", ops["FADD2"], ";  FFMA2", ops["FFMA2"],
+          "(explicit fma.rn.f32x2 only: exact division steps + the exact-integer vertical Sobel; a contracted blur would show ~400 FFMA2 and no FADD2)")
+    print("half-precision Sobel: HFMA2", ops["HFMA2"], " FHFMA (fma.rn.f32.f16)", ops["FHFMA"], " F2FP", ops["F2FP"])

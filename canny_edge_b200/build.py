@@ -28,6 +28,10 @@ NVCC_FLAGS = [
 ]
 
 
+# developer A/B builds: B200_NVCC_DEFS="-DF3_TAIL_IN_P1=0 ..." adds preprocessor definitions (part of the rebuild stamp)
+NVCC_FLAGS += os.environ.get("B200_NVCC_DEFS", "").split()
+
+
 def _nvcc() -> str:
     exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(exe):

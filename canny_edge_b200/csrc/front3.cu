@@ -131,7 +131,11 @@ front3_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
     uint16_t* s_ent = reinterpret_cast<uint16_t*>(smem + L.ent_off);
     uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem + L.bits_off);
     const bool sparse = p.kept_list != nullptr;                  // uniform: also fill parent[] and the weak-pixel list
-    float* s_np = s_temp + T0 * kTempPitch;   // n-plane (exact fp32 integers): the temp rows phase 1 refills next slab
+    // n-plane (exact fp32 integers, (SLAB+2) x 128 words): temp rows 0 .. SLAB-1.  The last 2R+2 temp lines (rows SLAB ..) — the ones
+    // the next slab's column pass needs again — are NOT under it, so nobody has to save them between the column pass and phase 3:
+    // the row pass of the next slab moves them to rows 0 .. 2R+1 (see there).
+    float* s_np = s_temp;
+    static_assert((SLAB + 2) * kNpPitch <= SLAB * kTempPitch, "the n-plane must end before the saved tail");
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -240,6 +244,15 @@ front3_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
         {
             const int srow = 32 * (warp >> 2) + lane;
             const int sp = warp & 3;
+            // The previous slab's last 2R+2 temp lines are needed again by this slab's column pass, at rows 0 .. 2R+1.  They sit exactly
+            // where the threads of slab rows SLAB-T0 .. SLAB-1 are about to write, so each of those threads first moves the 32 floats it
+            // is going to overwrite (no other thread touches them; the destination rows are only read after barrier (A)).
+            if (k > 0 && srow >= kSlab - T0) {
+                float4* dst = reinterpret_cast<float4*>(s_temp + (T0 + srow - kSlab) * kTempPitch + 2 * sp * kRunRow);
+                const float4* src = dst + kSlab * kTempPitch / 4;
+#pragma unroll
+                for (int q = 0; q < (2 * kRunRow) / 4; ++q) dst[q] = src[q];
+            }
             // needed bytes of a segment: [16*seg + lead, 16*seg + lead + 16 + 2R).  lead = 4*dq + DR with DR a compile-time constant
             // (x0 is a multiple of 4) and dq uniform over the CTA: load aligned 128-bit vectors, shift by dq WORDS with a uniform
             // switch, pick bytes with static selectors.
@@ -399,14 +412,6 @@ front3_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
         }
         __syncthreads();  // (B) VU rows 2..65 complete; every read of the temp buffer is done
 
-        // keep the last 2R+2 temp lines for the next slab (rows 64.. -> rows 0..): disjoint source / destination
-        if (k + 1 < n_slabs) {
-            constexpr int n4 = T0 * (kTC / 4);
-            for (int i = tid; i < n4; i += kThreads) {
-                const int r = i / (kTC / 4), q = i - r * (kTC / 4);
-                reinterpret_cast<float4*>(s_temp + r * kTempPitch)[q] = reinterpret_cast<const float4*>(s_temp + (kSlab + r) * kTempPitch)[q];
-            }
-        }
         // strips that contain image column -1 or W: the reference replicates horizontally for gx and drops for gy
         // (src/utils.cpp:117-147 vs :158-184).  gx only reads the v half of a neighbour word and gy only the u half, so ONE
         // virtual word {v = v[edge], u = 0} in the out-of-image column serves both.  (Uniform branch: the barrier is legal.)
@@ -417,9 +422,8 @@ front3_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
                 const int jw = W - (x0 - 2);                                    // column index of image x = W
                 if (jw >= 1 && jw < kTC) row[jw] = row[jw - 1] & 0xFFFF;
             }
+            __syncthreads();  // (B2) virtual columns patched
         }
-
-        __syncthreads();  // (B2) temp tail saved, virtual columns patched: temp rows T0.. are free, VU rows 0..65 final
 
         // ===================== phase 3a: horizontal half of Sobel, magnitude^2 plane, candidate lists =====================
         // n-plane row q (0..65) <-> VU buffer row q <-> global row y_base + q - 1; it lives in the free part of the temp buffer.
@@ -527,7 +531,7 @@ front3_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
                 const float* nrow = s_np + (rr + 1) * kNpPitch + c0;       // n[j] lives at word j - 1
                 const float2 n2 = *reinterpret_cast<const float2*>(nrow);
                 const float nc[2] = {n2.x, n2.y};
-                uint8_t* orow = out_base + (long long)rr * W + c0;
+                uint8_t* orow = out_base + (unsigned)(rr * W + c0);        // < 2^31: rr < 64, W < 2^24
                 // branch-free up to the local-maximum test so the two pixels' chains overlap
                 float na[2], nb[2];
                 bool pass[2];
@@ -595,7 +599,10 @@ front3_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
             }
             const int total = __shfl_sync(0xffffffffu, incl, 31);
             pend_base = 0;
-            if (total && lane == 0) pend_base = atomicAdd(p.kept_count, (unsigned int)total);
+            // (inline PTX: nvcc turns a plain atomicAdd in divergent code into its warp-aggregated form, whose shuffle needs the
+            // atomic's result at once — 2 % of the kernel's warp-time waited on that round trip)
+            if (total && lane == 0)
+                asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(pend_base) : "l"(p.kept_count), "r"((unsigned int)total) : "memory");
             pend_off = incl - cnt;
             // word tid <-> class row rr = tid >> 2, columns 32*(tid & 3) .. of the strip
             pend_g0 = (int)((long long)frame * p.out_frame_stride + (long long)(y_base + (tid >> 2) - p.plane_row0) * W + x0 + 32 * (tid & 3));

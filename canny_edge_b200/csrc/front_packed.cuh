@@ -81,7 +81,7 @@ __device__ __forceinline__ void gx2_gxy_h(uint32_t g, float& gx2, float& gxy) {
 // most one) + one correction in each direction, all in exact fp32 integer arithmetic; == ((int)sqrt((double)n))^2 of src/utils.cpp:212
 __device__ __forceinline__ float isqrt_sq_f(float n) {
     float s;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(s) : "f"(n));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(n));   // n is 0 or >= 1: nothing to flush, and no denormal scaling around the MUFU
     const float m = __fsub_rn(__fadd_rz(s, 8388608.0f), 8388608.0f);   // trunc(s)
     const float m2 = __fmul_rn(m, m);
     const float up = __fadd_rn(__fmaf_rn(m, 2.0f, m2), 1.0f);         // (m+1)^2

@@ -10,6 +10,6 @@ Layout:
 """
 from ._lib import CannyB200Error, LIB_PATH, load  # noqa: F401
 from .api import (  # noqa: F401
-    EDGE, NOEDGE, PI, Context, calculateXYGradient, canny_batch_device_ptr, canny_batch_host, createGaussianKernel,
+    EDGE, NOEDGE, PI, Context, calculateXYGradient, canny_batch_device_bgr_ptr, canny_batch_device_ptr, canny_batch_host, createGaussianKernel,
     cuda_canny, cuda_canny_bgr, cuda_gaussian, cuda_hysteresis, cuda_nonmaixmal_suppression, cuda_sobel, synth_host, synth_rows_host,
 )

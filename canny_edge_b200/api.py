@@ -59,6 +59,12 @@ class Context:
     def kernel_launches(self) -> int:
         return int(self._lib.b200_ctx_kernel_launches(self._h))
 
+    def front_kernel_stats(self):
+        """(launches of the specialised front kernels, launches of the generic one) so far."""
+        fast, gen = C.c_longlong(), C.c_longlong()
+        check(self._lib.b200_ctx_front_kernel_stats(self._h, C.byref(fast), C.byref(gen)))
+        return int(fast.value), int(gen.value)
+
     def close(self) -> None:
         if self._h:
             self._lib.b200_ctx_destroy(self._h)
@@ -186,6 +192,14 @@ def canny_batch_device_ptr(ctx: Context, d_frames: int, n: int, h: int, w: int, 
     """Raw device pointers (e.g. torch tensor.data_ptr()); asynchronous on the context's stream."""
     check(load().b200_canny_batch_device(_h(ctx), C.c_void_p(d_frames), n, h, w, C.c_float(sigma), int(min_val),
                                          int(max_val), C.c_void_p(d_edges)))
+
+
+def canny_batch_device_bgr_ptr(ctx: Context, d_bgr: int, n: int, h: int, w: int, sigma: float, min_val: int,
+                               max_val: int, d_edges: int) -> None:
+    """Device-resident interleaved B,G,R frames (n, h, w, 3) -> u8 edge maps; cvtColor(BGR2GRAY) (src/main.cpp:113) runs inside
+    the front kernel's staging when the shape allows (b200_canny_batch_device_bgr).  Asynchronous on the context's stream."""
+    check(load().b200_canny_batch_device_bgr(_h(ctx), C.c_void_p(d_bgr), n, h, w, C.c_float(sigma), int(min_val),
+                                             int(max_val), C.c_void_p(d_edges)))
 
 
 def synth_host(n: int, h: int, w: int, kind: int = 0, seed: int = 1234, first_frame: int = 0) -> np.ndarray:

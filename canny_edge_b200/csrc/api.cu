@@ -317,12 +317,14 @@ static int check_thresholds(int lo, int hi) {
 }
 
 // Runs front + hysteresis on device-resident frames [f0, f0+nf) using workspace slot `slot` on stream st.
+// bgr: d_in holds interleaved B,G,R frames (3 bytes per pixel) and the front kernel converts while staging (front3_bgr_supports)
 static int run_frames_device(b200_ctx* ctx, cudaStream_t st, int slot, const uint8_t* d_in, uint8_t* d_out, int nf, int h,
-                             int w, int lo, int hi, int16_t* blur, int16_t* mag, int16_t* ang, int16_t* nms) {
+                             int w, int lo, int hi, int16_t* blur, int16_t* mag, int16_t* ang, int16_t* nms, bool bgr = false) {
     const long long px = (long long)h * w;
     FrontParams fp;
     memset(&fp, 0, sizeof(fp));
-    fp.in = d_in; fp.in_frame_stride = px; fp.in_row0 = 0; fp.in_rows = h; fp.width = w; fp.height = h;
+    fp.in = d_in; fp.in_frame_stride = bgr ? 3 * px : px; fp.in_bgr = bgr ? 1 : 0;
+    fp.in_row0 = 0; fp.in_rows = h; fp.width = w; fp.height = h;
     fp.out_row0 = 0; fp.out_rows = h; fp.n_frames = nf; fp.cls = d_out; fp.out_frame_stride = px;
     fp.blur = blur; fp.mag = mag; fp.ang = ang; fp.nms = nms;
     fp.w = ctx->gauss.d_w; fp.count = ctx->gauss.d_count; fp.radius = ctx->gauss.radius;
@@ -353,9 +355,24 @@ static int run_frames_device(b200_ctx* ctx, cudaStream_t st, int slot, const uin
     hp.kept_thresh = (unsigned int)std::min<long long>(thresh, 0xffffffffLL);
     hp.parent = reinterpret_cast<int32_t*>(ctx->ws_parent[slot].ptr);
     hp.frame_stride = px; hp.rows = h; hp.width = w; hp.row0 = 0; hp.n_frames = nf;
+    // Small launches (the single-frame latency configuration) chain front -> link -> resolve by programmatic dependent launch: the
+    // next kernel's blocks are resident before its predecessor has drained.  Not for batch chunks: parked blocks would hold the
+    // SM resources the PREVIOUS chunk's hysteresis kernels (other stream) are meant to use next to the front kernel's CTAs.
+    static const int pdl_env = [] { const char* e = getenv("B200_CANNY_PDL"); return e ? atoi(e) : -1; }();
+    hp.pdl = pdl_env >= 0 ? pdl_env : ((long long)nf * px <= (4LL << 20) ? 1 : 0);
+    if (ctx->prof.on) hp.pdl = 0;   // per-kernel event pairs need the kernels apart
     CB_TRY(launch_hysteresis(ctx, st, hp));
     ctx->list_dirty[slot] = false;
     return B200_OK;
+}
+
+// whether launch_front takes these interleaved B,G,R frames directly (fused conversion) under the context's current sigma
+static bool bgr_fused_ok(const b200_ctx* ctx, const uint8_t* d_bgr, int h, int w) {
+    static const int force = [] { const char* e = getenv("B200_CANNY_FRONT"); return e ? atoi(e) : 0; }();
+    FrontParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.in = d_bgr; fp.in_frame_stride = 3LL * h * w; fp.width = w; fp.radius = ctx->gauss.radius;
+    return force == 0 && !ctx->gauss.tiny && front3_bgr_supports(fp);
 }
 
 // bytes of the weak-pixel list for nf frames of h x w: a counter block + one 32-bit entry per pixel (worst case: all weak)
@@ -732,8 +749,13 @@ int b200_canny_bgr(b200_ctx* ctx, const uint8_t* bgr, float sigma, int lo, int h
         h_src = reinterpret_cast<const uint8_t*>(ctx->host_in[0].ptr);
     }
     CB_CUDA(cudaMemcpyAsync(d_bgr, h_src, (size_t)px * 3, cudaMemcpyHostToDevice, st));
-    CB_TRY(launch_bgr_to_gray(ctx, st, d_bgr, pl.in, (size_t)px));
-    CB_TRY(run_frames_device(ctx, st, 0, pl.in, pl.cls, 1, h, w, lo, hi, nullptr, nullptr, nullptr, nullptr));
+    if (!gray_out && bgr_fused_ok(ctx, d_bgr, h, w)) {
+        // nobody wants the gray plane: the front kernel converts while it stages (no 4 B/px pass, no gray plane in HBM)
+        CB_TRY(run_frames_device(ctx, st, 0, d_bgr, pl.cls, 1, h, w, lo, hi, nullptr, nullptr, nullptr, nullptr, /*bgr=*/true));
+    } else {
+        CB_TRY(launch_bgr_to_gray(ctx, st, d_bgr, pl.in, (size_t)px));
+        CB_TRY(run_frames_device(ctx, st, 0, pl.in, pl.cls, 1, h, w, lo, hi, nullptr, nullptr, nullptr, nullptr));
+    }
     if (!fast) {
         CB_TRY(launch_expand_u8_to_i16(ctx, st, pl.cls, pl.p16[4], (size_t)px));
         if (gray_out) CB_CUDA(cudaMemcpyAsync(gray_out, pl.in, (size_t)px, cudaMemcpyDeviceToHost, st));
@@ -760,8 +782,10 @@ int b200_canny_bgr(b200_ctx* ctx, const uint8_t* bgr, float sigma, int lo, int h
 }
 
 // ---- batched --------------------------------------------------------------------------------------------
-int b200_canny_batch_device(b200_ctx* ctx, const uint8_t* d_frames, int n_frames, int h, int w, float sigma, int lo,
-                            int hi, uint8_t* d_edges) {
+// bpp: bytes per input pixel — 1 gray, 3 interleaved B,G,R (converted by the front kernel while staging when it can, else chunk by
+// chunk into a gray scratch plane first)
+static int batch_device_impl(b200_ctx* ctx, const uint8_t* d_frames, int n_frames, int h, int w, float sigma, int lo, int hi,
+                             uint8_t* d_edges, int bpp) {
     CB_TRY(check_image(d_frames, d_edges, h, w));
     CB_TRY(check_thresholds(lo, hi));
     if (n_frames <= 0) { set_error("n_frames must be positive"); return B200_ERR_INVALID_ARG; }
@@ -775,28 +799,46 @@ int b200_canny_batch_device(b200_ctx* ctx, const uint8_t* d_frames, int n_frames
     // waiting (same slot) for those hysteresis kernels (226 against 219 Gpix/s with two slots; running the hysteresis kernels on
     // high-priority streams on top of that measured 222)
     const int n_slots = std::min(3, n_chunks);
+    const bool bgr = bpp == 3;
+    const bool fused = bgr && bgr_fused_ok(ctx, d_frames, h, w);
     for (int s = 0; s < n_slots; ++s) {
         CB_TRY(ensure_ws(ctx->ws_parent[s], (size_t)px * 4 * (size_t)chunk));
         CB_TRY(ensure_ws(ctx->ws_list[s], list_bytes(chunk, h, w)));
+        if (bgr && !fused) CB_TRY(ensure_ws(ctx->dev_in[s], (size_t)px * (size_t)chunk));   // gray scratch of one chunk
     }
-    if (n_slots == 1) {
-        CB_TRY(run_frames_device(ctx, ctx->stream, 0, d_frames, d_edges, n_frames, h, w, lo, hi, nullptr, nullptr, nullptr, nullptr));
-        return B200_OK;
-    }
+    auto run_chunk = [&](cudaStream_t st, int s, int f0, int nf) -> int {
+        const uint8_t* src = d_frames + (long long)f0 * px * bpp;
+        if (bgr && !fused) {
+            uint8_t* gray = reinterpret_cast<uint8_t*>(ctx->dev_in[s].ptr);
+            CB_TRY(launch_bgr_to_gray(ctx, st, src, gray, (size_t)px * (size_t)nf));
+            src = gray;
+        }
+        return run_frames_device(ctx, st, s, src, d_edges + (long long)f0 * px, nf, h, w, lo, hi, nullptr, nullptr, nullptr, nullptr, fused);
+    };
+    if (n_slots == 1) return run_chunk(ctx->stream, 0, 0, n_frames);
     // the side streams take the chunks in turn so one chunk's tail waves overlap the next chunks' heads
     CB_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
     for (int s = 0; s < n_slots; ++s) CB_CUDA(cudaStreamWaitEvent(ctx->side[s], ctx->ev_fork, 0));
     for (int c = 0; c < n_chunks; ++c) {
         const int f0 = c * chunk, nf = std::min(chunk, n_frames - f0);
         const int s = c % n_slots;
-        CB_TRY(run_frames_device(ctx, ctx->side[s], s, d_frames + (long long)f0 * px, d_edges + (long long)f0 * px, nf, h, w, lo,
-                                 hi, nullptr, nullptr, nullptr, nullptr));
+        CB_TRY(run_chunk(ctx->side[s], s, f0, nf));
     }
     for (int s = 0; s < n_slots; ++s) {
         CB_CUDA(cudaEventRecord(ctx->ev_join[s], ctx->side[s]));
         CB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[s], 0));
     }
     return B200_OK;
+}
+
+int b200_canny_batch_device(b200_ctx* ctx, const uint8_t* d_frames, int n_frames, int h, int w, float sigma, int lo,
+                            int hi, uint8_t* d_edges) {
+    return batch_device_impl(ctx, d_frames, n_frames, h, w, sigma, lo, hi, d_edges, 1);
+}
+
+int b200_canny_batch_device_bgr(b200_ctx* ctx, const uint8_t* d_bgr, int n_frames, int h, int w, float sigma, int lo,
+                                int hi, uint8_t* d_edges) {
+    return batch_device_impl(ctx, d_bgr, n_frames, h, w, sigma, lo, hi, d_edges, 3);
 }
 
 // Host buffers in, host buffers out: frames -> 0 / 255 edge maps, as bytes (edges8) or as the reference's int16 (edges16).

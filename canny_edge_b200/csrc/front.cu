@@ -525,6 +525,25 @@ int make_input_tensor_map(const FrontParams& p, int box_cols, int box_rows, CUte
     return B200_OK;
 }
 
+// Interleaved B,G,R frames as a tensor of 32-bit elements (a box row of a u8 map holds at most 256 bytes; the staged row is 528):
+// 3*width/4 elements per row, out-of-range elements zero-filled like the gray map's.
+int make_bgr_tensor_map(const FrontParams& p, int box_words, int box_rows, CUtensorMap* tmap) {
+    memset(tmap, 0, sizeof(*tmap));
+    if (get_encode_fn() == nullptr) { set_error("cuTensorMapEncodeTiled is not available"); return B200_ERR_UNSUPPORTED; }
+    const cuuint64_t dims[3] = {(cuuint64_t)(3 * (long long)p.width / 4), (cuuint64_t)p.in_rows, (cuuint64_t)p.n_frames};
+    const cuuint64_t strides[2] = {(cuuint64_t)(3 * (long long)p.width), (cuuint64_t)p.in_frame_stride};
+    const cuuint32_t box[3] = {(cuuint32_t)box_words, (cuuint32_t)box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = get_encode_fn()(tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(p.in), dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for BGR %dx%dx%d", (int)r, p.width, p.in_rows, p.n_frames);
+        return B200_ERR_CUDA;
+    }
+    return B200_OK;
+}
+
 static int launch_front_v1(b200_ctx* ctx, cudaStream_t st, const FrontParams& p_in) {
     FrontParams p = p_in;
     const int radius = p.radius;
@@ -562,6 +581,10 @@ int launch_front(b200_ctx* ctx, cudaStream_t st, const FrontParams& p_in, bool* 
     static const int force = [] { const char* e = getenv("B200_CANNY_FRONT"); return e ? atoi(e) : 0; }();
     const bool force_v1 = force == 1;
     const bool spill = p.blur || p.mag || p.ang || p.nms;
+    if (p.in_bgr && (force_v1 || force == 2 || spill || ctx->gauss.tiny || !front3_bgr_supports(p))) {
+        set_error("interleaved B,G,R input is only taken by the fused front kernel (callers check front3_bgr_supports)");
+        return B200_ERR_UNSUPPORTED;
+    }
     if (!force_v1 && !spill && !ctx->gauss.tiny && front2_supports(radius)) {
         // the sparse hand-over lists KEPT pixels; with minVal <= 0 suppressed pixels are candidates too (src/utils.cpp:328), so the
         // whole-plane labelling has to run

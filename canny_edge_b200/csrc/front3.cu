@@ -63,12 +63,16 @@ struct SmemLayout {
 // radius would then push a CTA past half an SM's shared memory — with one buffer the next slab is requested as soon as the row
 // pass has read this one and lands during the column pass and phase 3
 __host__ __device__ constexpr int in_bufs_for(int radius) { return radius > 9 ? 1 : 2; }
-__host__ __device__ constexpr SmemLayout smem_layout(int radius, int slab) {
+// bgr: the kernel is fed interleaved B,G,R bytes.  A slab of them (slab rows x 3 * in_pitch bytes) lands by TMA in VU rows 2.. —
+// free between the end of phase 3 and the next column pass — and is converted into ONE staged gray buffer, so the variant needs
+// less shared memory than the gray one, not more.
+__host__ __device__ constexpr SmemLayout smem_layout(int radius, int slab, bool bgr = false) {
     SmemLayout L{};
     int o = 0;
-    L.in_off = o;   o += in_bufs_for(radius) * slab * in_pitch_for(radius);
+    L.in_off = o;   o += (bgr ? 1 : in_bufs_for(radius)) * slab * in_pitch_for(radius);
     o = (o + 127) & ~127;
     L.temp_off = o; o += temp_rows_for(radius, slab) * kTempPitch * 4;
+    if (bgr) while ((o + 2 * kVuPitch * 4) & 127) o += 16;     // the TMA destination (VU row 2) on a 128 B boundary
     L.vu_off = o;   o += (slab + 2) * kVuPitch * 4;
     L.ent_off = o;  o += slab * 64 * 2;                        // candidate lists: at most one 16-bit entry per (class row, lane, pixel pair)
     L.bits_off = o; o += slab * 4 * 4;                         // weak-pixel bitmap of the slab's class rows: 4 words per row
@@ -101,11 +105,23 @@ constexpr int kBias4 = (int)(4u * 0x4B000000u);  // 4 * bias mod 2^32 = 0x2C0000
 
 using namespace pk;
 
+// Predicated stores for phase 3b: nvcc turns `if (keep) *p = v;` into a branch around the store (and sinks the address arithmetic
+// into it); four pixels per round would be eight short divergent regions.
+__device__ __forceinline__ void st_u8_if(bool on, uint8_t* ptr, uint32_t v) {
+    asm volatile("{ .reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t@q st.global.u8 [%1], %2; }" ::"r"((int)on), "l"(ptr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_u32_if(bool on, int32_t* ptr, uint32_t v) {
+    asm volatile("{ .reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t@q st.global.u32 [%1], %2; }" ::"r"((int)on), "l"(ptr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_or_shared_if(bool on, uint32_t* ptr, uint32_t v) {
+    asm volatile("{ .reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t@q red.shared.or.b32 [%1], %2; }" ::"r"((int)on), "r"(smem_u32(ptr)), "r"(v) : "memory");
+}
+
 // Register cap: 96 (no spills at any radius; the kernel takes 128 when left alone).  Two resident CTAs then leave a quarter of the
 // register file free, so blocks of the small latency-bound hysteresis kernels of the PREVIOUS chunk (other stream) become
 // resident next to them instead of waiting for a front CTA to retire: the front kernel alone gets 1.7 % slower, the chunk
 // pipeline 2.3 % faster on the bench frames and 8 % faster on photographic content (112 / 104 / 88 / 80 measured too: 96 wins).
-template <int R, bool USE_TMA, int DIV, int SLAB>
+template <int R, bool USE_TMA, int DIV, int SLAB, bool BGR = false>
 __global__ void __maxnreg__(SLAB == 64 ? 96 : 64)
 front3_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -117,8 +133,9 @@ front3_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
     constexpr int kEntPerWarp = (SLAB / 8) * 64;
     static_assert(SLAB == 64, "row/column pass mappings are written for 64-row slabs");
     static_assert(2 * R + 2 <= SLAB, "the saved tail must not overlap the rows it is copied from");
-    constexpr SmemLayout L = smem_layout(R, SLAB);
+    constexpr SmemLayout L = smem_layout(R, SLAB, BGR);
     constexpr int in_pitch = in_pitch_for(R);
+    static_assert(!BGR || (USE_TMA && 3 * in_pitch == kVuPitch * 4 && R <= 9), "BGR staging: one TMA box row per VU row, 160 staged columns");
     constexpr int T0 = 2 * R + 2;  // temp buffer row of the first row of the current slab
 
     unsigned char* s_in = smem + L.in_off;
@@ -139,6 +156,9 @@ front3_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
+    // latency path: the list-driven hysteresis kernel behind this one may be launched programmatically (HystParams::pdl); it parks
+    // on griddepcontrol.wait until this grid has completed.  A no-op for ordinary launches.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     // ---- which strip / band / frame ----
     const int strip = blockIdx.x, band = blockIdx.y, frame = blockIdx.z;
@@ -183,7 +203,7 @@ front3_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
     const uint8_t* in_frame = p.in + (long long)frame * p.in_frame_stride;
     constexpr uint32_t slab_bytes = (uint32_t)(kSlab * in_pitch);
 
-    constexpr int kInBufs = in_bufs_for(R);
+    constexpr int kInBufs = BGR ? 1 : in_bufs_for(R);
     auto issue_slab = [&](int k) {
         const int gy = in_y0 + k * kSlab;
         unsigned char* dst = s_in + (k % kInBufs) * slab_bytes;
@@ -205,8 +225,49 @@ front3_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
             }
         }
     };
+    // ---- BGR input (cvtColor(frame, gray, COLOR_BGR2GRAY) of src/main.cpp:113, folded into the staging) ----
+    // One thread issues the TMA of a slab of interleaved bytes (the tensor map sees 32-bit elements, 3W/4 per row; rows and columns
+    // outside the image arrive as zeros, whose gray value is 0: the same zero fill the gray path relies on) into VU rows 2 .. SLAB+1.
+    unsigned char* s_bgr = reinterpret_cast<unsigned char*>(s_vu + 2 * kVuPitch);
+    auto issue_bgr = [&](int k) {   // one thread
+        mbar_expect_tx(bar0, 3u * slab_bytes);
+        tma_load_3d(smem_u32(s_bgr), &tmap, bar0, (in_x0 * 3) / 4, in_y0 + k * kSlab - p.in_row0, frame);
+    };
+    // OpenCV's 8-bit BGR2GRAY is fixed point: (B*3735 + G*19235 + R*9798 + 2^14) >> 15.  With doubled coefficients the result sits
+    // in byte 2 of 2*(..) + 2^15 (< 2^24), and the three products of a pixel are two 16x8-bit dot products (dp2a) whichever way
+    // its bytes straddle the 32-bit words.  A task = 8 pixels = 24 bytes -> two gray words; SLAB x 20 tasks = 5 per thread cover
+    // the 160 staged columns the row pass reads.
+    auto convert_bgr = [&]() {
+        constexpr uint32_t cB = 2 * 3735, cG = 2 * 19235, cR = 2 * 9798;
+        constexpr uint32_t kBG = cB | (cG << 16), kR0 = cR, k0B = cB << 16, kGR = cG | (cR << 16), kHalf = 32768;
+        auto gray4 = [&](uint32_t w0, uint32_t w1, uint32_t w2) {   // B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
+            const uint32_t g0 = __dp2a_hi(kR0, w0, __dp2a_lo(kBG, w0, kHalf));
+            const uint32_t g1 = __dp2a_lo(kGR, w1, __dp2a_hi(k0B, w0, kHalf));
+            const uint32_t g2 = __dp2a_lo(kR0, w2, __dp2a_hi(kBG, w1, kHalf));
+            const uint32_t g3 = __dp2a_hi(kGR, w2, __dp2a_lo(k0B, w2, kHalf));
+            return __byte_perm(__byte_perm(g0, g1, 0x0062), __byte_perm(g2, g3, 0x0062), 0x5410);
+        };
+        constexpr int kHU = 20;
+        static_assert((kSlab * kHU) % kThreads == 0, "whole rounds");
+#pragma unroll
+        for (int t0 = 0; t0 < kSlab * kHU; t0 += kThreads) {
+            const int t = t0 + tid;
+            const int r = t / kHU, hu = t - r * kHU;
+            const uint2* src = reinterpret_cast<const uint2*>(s_bgr + r * (3 * in_pitch) + hu * 24);
+            const uint2 a = src[0], b = src[1], c = src[2];
+            *reinterpret_cast<uint2*>(s_in + r * in_pitch + hu * 8) = make_uint2(gray4(a.x, a.y, b.x), gray4(b.y, c.x, c.y));
+        }
+    };
 
-    if (USE_TMA) {
+    if (BGR) {
+        // slab 0 is converted before the loop; from then on slab k+1 lands during the row pass of slab k and is converted right
+        // after it (the single gray buffer is free by then), before the column pass takes the VU rows back
+        if (tid == 0) issue_bgr(0);
+        mbar_wait(bar0, 0);
+        convert_bgr();
+        __syncthreads();
+        if (n_slabs > 1 && tid == 0) issue_bgr(1);
+    } else if (USE_TMA) {
         issue_slab(0);
         if (kInBufs > 1 && n_slabs > 1) issue_slab(1);
     }
@@ -229,7 +290,9 @@ front3_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
 
     for (int k = 0; k < n_slabs; ++k) {
         const int I_k = in_y0 + k * kSlab;  // global row of this slab's first input line
-        if (USE_TMA) {
+        if (BGR) {
+            // the staged gray slab was converted in the previous iteration (or before the loop)
+        } else if (USE_TMA) {
             mbar_wait(bar0 + 8 * (k % kInBufs), (uint32_t)((k / kInBufs) & 1));
         } else {
             issue_slab(k);
@@ -338,7 +401,15 @@ front3_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
         }
         if (sparse) flush_pending();
         __syncthreads();  // (A) this slab's temp lines are complete; staged buffer k&1 is free again
-        if (USE_TMA && k + kInBufs < n_slabs) issue_slab(k + kInBufs);
+        if (BGR) {
+            if (k + 1 < n_slabs) {
+                mbar_wait(bar0, (uint32_t)((k + 1) & 1));
+                convert_bgr();
+                __syncthreads();  // (A') the gray slab of the next iteration is staged; the VU rows belong to the column pass again
+            }
+        } else if (USE_TMA && k + kInBufs < n_slabs) {
+            issue_slab(k + kInBufs);
+        }
 
         // ===================== phase 2: column blur f32 -> int (src/utils.cpp:52-64) + vertical half of Sobel, two columns per thread ====
         // thread = (columns c = tid&63 and c + 64; row group tid>>6).  Blurred rows Bg(o) = I_k - R - 2 + 16*group + o, o = 0..17, from temp
@@ -516,69 +587,86 @@ front3_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
         __syncthreads();  // (C1) n-plane complete; the zero words are ordered before phase 3b's byte stores
 
         // ===================== phase 3b: direction, NMS and thresholds for the candidates only =====================
+        // A lane takes TWO list entries (four pixels) per round and everything up to the stores is branch-free, so the four
+        // dependent chains (entry -> Sobel words -> direction -> neighbours -> truncated-magnitude test) overlap: with 16 warps
+        // per SM this phase is bound by those chains, not by issue slots.
         {
             const long long out_off = (long long)frame * p.out_frame_stride + (long long)(y_base - p.plane_row0) * W + (x0 - 2) + 1;
             uint8_t* out_base = p.cls + out_off;
             int32_t* par_base = p.parent + out_off;                           // only dereferenced when `sparse`
             const int idx_base = (int)out_off;                                // launch-relative pixel index of (class row 0, column j = 1)
-            for (int i = lane; i < my_count; i += 32) {
-                const int ent = my_ent[i];
-                const int rr = ent >> 6, c0 = 2 * (ent & 63);              // pixels j = c0 + 1 and c0 + 2 of class row rr
-                const int32_t* vrow = s_vu + (rr + 1) * kVuPitch + c0;     // VU words j-1 .. j+2 = c0 .. c0+3
-                const uint2 qa = *reinterpret_cast<const uint2*>(vrow);
-                const uint2 qb = *reinterpret_cast<const uint2*>(vrow + 2);
-                const uint32_t wd[4] = {qa.x, qa.y, qb.x, qb.y};
-                const float* nrow = s_np + (rr + 1) * kNpPitch + c0;       // n[j] lives at word j - 1
-                const float2 n2 = *reinterpret_cast<const float2*>(nrow);
-                const float nc[2] = {n2.x, n2.y};
-                uint8_t* orow = out_base + (unsigned)(rr * W + c0);        // < 2^31: rr < 64, W < 2^24
-                // branch-free up to the local-maximum test so the two pixels' chains overlap
-                float na[2], nb[2];
-                bool pass[2];
+            for (int i = lane; i < my_count; i += 64) {
+                int ent[2];
+                ent[0] = my_ent[i];
+                const bool have1 = i + 32 < my_count;
+                ent[1] = have1 ? my_ent[i + 32] : ent[0];
+                float nc[2][2], na[2][2], nb[2][2];
+                bool pass[2][2];
+                int rel[2];
+                uint8_t* orow[2];
+                int32_t* prow[2];
+                uint32_t* bits[2][2];
+                uint32_t mask[2][2];
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const float n = nc[e];
-                    float gx2, pxy;
-                    gx2_gxy_h(sobel_h(wd[e], wd[e + 1], wd[e + 2]), gx2, pxy);
-                    // direction_code() of canny_math.h in product form (same integer tests as src/utils.cpp:215-231's bins), on
-                    // exact fp32 integers:
-                    //   0   <=> (ay+ax)^2 < 2ax^2           <=> ax^2 - ay^2 > 2 ax ay
-                    //   90  <=> ay > ax and (ay-ax)^2 > 2ax^2 <=> ay^2 - ax^2 > 2 ax ay
-                    //   else a diagonal: 45 when gx and gy have the same sign (gx*gy > 0; both are non-zero there).
-                    // gx = gy = 0 lands on "45" instead of 0, which cannot change the class: such a pixel is a candidate only when
-                    // minVal <= 0, and then kept and suppressed pixels get the same class (see fill_thresholds()).
-                    const float dd = __fmaf_rn(gx2, 2.0f, -n);   // ax^2 - ay^2  (n = ax^2 + ay^2)
-                    const float p2 = 2.0f * fabsf(pxy);
-                    const bool is0 = dd > p2;
-                    const bool is90 = -dd > p2;
-                    const bool same = pxy >= 0.f;
-                    // neighbour pair along the quantised direction (src/utils.cpp:253-304); out-of-image neighbours hold -1
-                    const int off = is0 ? 1 : (is90 ? kNpPitch : (same ? (1 - kNpPitch) : (1 + kNpPitch)));
-                    na[e] = nrow[e + off];
-                    nb[e] = nrow[e - off];
-                    const int j = c0 + 1 + e;
-                    pass[e] = (n >= lo2f) && (j >= 2) && (j <= kTC - 3) && (na[e] < n) && (nb[e] < n);   // j = 1, j >= 126: neighbour-only columns
+                for (int u = 0; u < 2; ++u) {
+                    const int rr = ent[u] >> 6, c0 = 2 * (ent[u] & 63);        // pixels j = c0 + 1 and c0 + 2 of class row rr
+                    rel[u] = rr * W + c0;                                      // < 2^31: rr < 64, W < 2^24
+                    orow[u] = out_base + (unsigned)rel[u];
+                    prow[u] = par_base + (unsigned)rel[u];
+                    const int32_t* vrow = s_vu + (rr + 1) * kVuPitch + c0;     // VU words j-1 .. j+2 = c0 .. c0+3
+                    const uint2 qa = *reinterpret_cast<const uint2*>(vrow);
+                    const uint2 qb = *reinterpret_cast<const uint2*>(vrow + 2);
+                    const uint32_t wd[4] = {qa.x, qa.y, qb.x, qb.y};
+                    const float* nrow = s_np + (rr + 1) * kNpPitch + c0;       // n[j] lives at word j - 1
+                    const float2 n2 = *reinterpret_cast<const float2*>(nrow);
+                    nc[u][0] = n2.x; nc[u][1] = n2.y;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float n = nc[u][e];
+                        float gx2, pxy;
+                        gx2_gxy_h(sobel_h(wd[e], wd[e + 1], wd[e + 2]), gx2, pxy);
+                        // direction_code() of canny_math.h in product form (same integer tests as src/utils.cpp:215-231's bins), on
+                        // exact fp32 integers:
+                        //   0   <=> (ay+ax)^2 < 2ax^2           <=> ax^2 - ay^2 > 2 ax ay
+                        //   90  <=> ay > ax and (ay-ax)^2 > 2ax^2 <=> ay^2 - ax^2 > 2 ax ay
+                        //   else a diagonal: 45 when gx and gy have the same sign (gx*gy > 0; both are non-zero there).
+                        // gx = gy = 0 lands on "45" instead of 0, which cannot change the class: such a pixel is a candidate only when
+                        // minVal <= 0, and then kept and suppressed pixels get the same class (see fill_thresholds()).
+                        const float dd = __fmaf_rn(gx2, 2.0f, -n);   // ax^2 - ay^2  (n = ax^2 + ay^2)
+                        const float p2 = 2.0f * fabsf(pxy);
+                        const bool is0 = dd > p2;
+                        const bool is90 = -dd > p2;
+                        const bool same = pxy >= 0.f;
+                        // neighbour pair along the quantised direction (src/utils.cpp:253-304); out-of-image neighbours hold -1
+                        const int off = is0 ? 1 : (is90 ? kNpPitch : (same ? (1 - kNpPitch) : (1 + kNpPitch)));
+                        na[u][e] = nrow[e + off];
+                        nb[u][e] = nrow[e - off];
+                        const int j = c0 + 1 + e;
+                        pass[u][e] = (n >= lo2f) && (j >= 2) && (j <= kTC - 3);   // j = 1, j >= 126: neighbour-only columns
+                        const int col = j - 2;                                // class column within the strip (bitmap: 4 words per row)
+                        bits[u][e] = &s_bits[rr * 4 + ((col >> 5) & 3)];
+                        mask[u][e] = 1u << (col & 31);
+                    }
                 }
+                pass[1][0] = pass[1][0] && have1;
+                pass[1][1] = pass[1][1] && have1;
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    if (pass[e]) {
+                for (int u = 0; u < 2; ++u) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
                         // the reference compares truncated magnitudes: keep iff floor(sqrt(n_nb)) < floor(sqrt(n)) <=> n_nb < mag^2
-                        const float n = nc[e];
+                        // (n_nb < mag^2 <= n implies the plain local-maximum test; n = -1 of an out-of-image column gives NaN: false)
+                        const float n = nc[u][e];
                         const float m2 = isqrt_sq_f(n);
-                        if (na[e] < m2 && nb[e] < m2) {
-                            const bool strong = n >= hi2f;
-                            orow[e] = strong ? (uint8_t)255 : (uint8_t)1;
-                            if (sparse && !strong) {
-                                // hand-over to the list-driven hysteresis kernels: only WEAK pixels need any work there (a strong
-                                // pixel is final; its neighbours find it through the class map).  The weak pixel gets its union-
-                                // find slot (itself) and a bit in the slab's bitmap, from which the list entries are made once
-                                // the slab is finished
-                                const int rel = rr * W + c0 + e;
-                                par_base[rel] = idx_base + rel;
-                                const int col = c0 + e - 1;                   // class column within the strip: j - 2
-                                atomicOr(&s_bits[rr * 4 + (col >> 5)], 1u << (col & 31));
-                            }
-                        }
+                        const bool keep = pass[u][e] && (na[u][e] < m2) && (nb[u][e] < m2);
+                        const bool strong = n >= hi2f;
+                        st_u8_if(keep, orow[u] + e, strong ? 255u : 1u);
+                        // hand-over to the list-driven hysteresis kernels: only WEAK pixels need any work there (a strong pixel is
+                        // final; its neighbours find it through the class map).  The weak pixel gets its union-find slot (itself)
+                        // and a bit in the slab's bitmap, from which the list entries are made once the slab is finished
+                        const bool weak = sparse && keep && !strong;
+                        st_u32_if(weak, prow[u] + e, (uint32_t)(idx_base + rel[u] + e));
+                        red_or_shared_if(weak, bits[u][e], mask[u][e]);
                     }
                 }
             }
@@ -608,7 +696,21 @@ front3_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
             pend_g0 = (int)((long long)frame * p.out_frame_stride + (long long)(y_base + (tid >> 2) - p.plane_row0) * W + x0 + 32 * (tid & 3));
         }
         // VU rows 64,65 (blurred-row neighbours of the next slab's first class rows) -> rows 0,1
-        if (k + 1 < n_slabs) s_vu[(tid >> 7) * kVuPitch + (tid & 127)] = s_vu[(kSlab + (tid >> 7)) * kVuPitch + (tid & 127)];
+        if (!BGR) {
+            if (k + 1 < n_slabs) s_vu[(tid >> 7) * kVuPitch + (tid & 127)] = s_vu[(kSlab + (tid >> 7)) * kVuPitch + (tid & 127)];
+        } else if (k + 1 < n_slabs && warp == 0) {
+            // BGR: the slab after the next one is about to land on VU rows 2 .. SLAB+1, so ONE warp moves the two rows and then
+            // issues that TMA (every warp's phase 3 reads are behind barrier (C))
+            const uint4 a = *reinterpret_cast<const uint4*>(s_vu + kSlab * kVuPitch + 4 * lane);
+            const uint4 b = *reinterpret_cast<const uint4*>(s_vu + (kSlab + 1) * kVuPitch + 4 * lane);
+            *reinterpret_cast<uint4*>(s_vu + 4 * lane) = a;
+            *reinterpret_cast<uint4*>(s_vu + kVuPitch + 4 * lane) = b;
+            __syncwarp();
+            if (k + 2 < n_slabs && lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue_bgr(k + 2);
+            }
+        }
         // the next iteration's barrier (A) orders this copy before phase 2 rewrites rows 2..65 and phase 3 reads rows 0,1
     }
     if (sparse) flush_pending();
@@ -619,18 +721,18 @@ front3_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int R, bool USE_TMA, int DIV, int SLAB>
+template <int R, bool USE_TMA, int DIV, int SLAB, bool BGR = false>
 static int launch_one3(b200_ctx* ctx, cudaStream_t st, const FrontParams& p, const CUtensorMap& tmap, dim3 grid) {
-    const f3::SmemLayout L = f3::smem_layout(R, SLAB);
+    const f3::SmemLayout L = f3::smem_layout(R, SLAB, BGR);
     static bool configured[64] = {false};  // per instantiation, per device
     if (!configured[ctx->device & 63]) {
-        CB_CUDA(cudaFuncSetAttribute(f3::front3_kernel<R, USE_TMA, DIV, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-        CB_CUDA(cudaFuncSetAttribute(f3::front3_kernel<R, USE_TMA, DIV, SLAB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CB_CUDA(cudaFuncSetAttribute(f3::front3_kernel<R, USE_TMA, DIV, SLAB, BGR>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        CB_CUDA(cudaFuncSetAttribute(f3::front3_kernel<R, USE_TMA, DIV, SLAB, BGR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured[ctx->device & 63] = true;
     }
     {
         ProfScope ps(ctx, st, 0);
-        f3::front3_kernel<R, USE_TMA, DIV, SLAB><<<grid, f3::kThreads, L.total, st>>>(p, tmap);
+        f3::front3_kernel<R, USE_TMA, DIV, SLAB, BGR><<<grid, f3::kThreads, L.total, st>>>(p, tmap);
     }
     CB_CUDA(cudaGetLastError());
     ctx->launches++;
@@ -646,6 +748,26 @@ static int launch_r3(b200_ctx* ctx, cudaStream_t st, const FrontParams& p, const
     }
     // generic staging (odd widths) is not a throughput path: one instantiation, the always-valid division
     return launch_one3<R, false, 5, SLAB>(ctx, st, p, tmap, grid);
+}
+
+// interleaved B,G,R input: TMA only, the three exact divisions
+template <int R, int SLAB>
+static int launch_r3_bgr(b200_ctx* ctx, cudaStream_t st, const FrontParams& p, const CUtensorMap& tmap, dim3 grid, int div) {
+    if (div == 1) return launch_one3<R, true, 1, SLAB, true>(ctx, st, p, tmap, grid);
+    if (div == 3) return launch_one3<R, true, 3, SLAB, true>(ctx, st, p, tmap, grid);
+    return launch_one3<R, true, 5, SLAB, true>(ctx, st, p, tmap, grid);
+}
+
+// The fused-conversion variant exists for half-windows up to 9 (one staged input buffer is what larger ones use anyway) and needs
+// the TMA path: rows of 3W bytes on 16 B boundaries.
+bool front3_bgr_supports(const FrontParams& p) {
+    static const bool tma_env_off = [] { const char* e = getenv("B200_CANNY_NO_TMA"); return e && e[0] == '1'; }();
+    static const bool fuse_off = [] { const char* e = getenv("B200_CANNY_BGR_FUSED"); return e && e[0] == '0'; }();
+    switch (p.radius) {
+        case 2: case 3: case 5: case 6: case 9: break;
+        default: return false;
+    }
+    return !tma_env_off && !fuse_off && (p.width % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.in) & 15) == 0) && (p.in_frame_stride % 16 == 0);
 }
 
 bool front3_supports(int radius) {
@@ -688,9 +810,20 @@ int launch_front3(b200_ctx* ctx, cudaStream_t st, const FrontParams& p_in) {
     dim3 grid(strips, p.tiles_y, p.n_frames);
     CUtensorMap tmap;
     bool use_tma = false;
-    CB_TRY(make_input_tensor_map(p, f3::in_pitch_for(radius), slab, &tmap, &use_tma));
     const int div3 = ctx->gauss.div_mode;
     p.div_c = ctx->gauss.div_c;
+    if (p.in_bgr) {
+        if (!front3_bgr_supports(p)) { set_error("fused BGR input needs width %% 16 == 0, 16-byte aligned frames and a half-window <= 9"); return B200_ERR_UNSUPPORTED; }
+        CB_TRY(make_bgr_tensor_map(p, 3 * f3::in_pitch_for(radius) / 4, slab, &tmap));
+        switch (radius) {
+            case 2: return launch_r3_bgr<2, 64>(ctx, st, p, tmap, grid, div3);
+            case 3: return launch_r3_bgr<3, 64>(ctx, st, p, tmap, grid, div3);
+            case 5: return launch_r3_bgr<5, 64>(ctx, st, p, tmap, grid, div3);
+            case 6: return launch_r3_bgr<6, 64>(ctx, st, p, tmap, grid, div3);
+            default: return launch_r3_bgr<9, 64>(ctx, st, p, tmap, grid, div3);
+        }
+    }
+    CB_TRY(make_input_tensor_map(p, f3::in_pitch_for(radius), slab, &tmap, &use_tma));
     switch (radius) {
         case 2: return launch_r3<2, 64>(ctx, st, p, tmap, grid, use_tma, div3);
         case 3: return launch_r3<3, 64>(ctx, st, p, tmap, grid, use_tma, div3);

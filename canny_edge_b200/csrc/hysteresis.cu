@@ -263,8 +263,16 @@ ccl_final_kernel(const HystParams p) {
 // the two diagonals reach the pixel through S's own links) are united with it, so every weak-weak pair is visited exactly once,
 // from its earlier endpoint in raster order.  The pair (0,1)-(1,0) of the GLOBAL image is skipped in both directions (see the
 // file header): the one-way link is applied by the last block of this kernel, below.
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may become resident
+// while its predecessor in the stream still runs; griddepcontrol.wait then blocks until that grid has completed and its writes are
+// visible.  launch_dependents lets the NEXT kernel in the stream do the same with this one.  Both are no-ops in ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __global__ void __launch_bounds__(256)
 ccl_sparse_link_kernel(const HystParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     const unsigned int n_all = p.ctr[0];
     const unsigned int n = n_all;
     const uint32_t* const walk = p.list;
@@ -338,6 +346,7 @@ __global__ void list_retire_kernel(unsigned int* ctr, unsigned int* h_kept, unsi
 // every weak pixel chases its root: 255 when the component hangs under SUPER, else 0
 __global__ void __launch_bounds__(256)
 ccl_sparse_resolve_kernel(const HystParams p) {
+    pdl_wait();
     const unsigned int n = p.ctr[2];
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const unsigned int g = p.list[i];
@@ -358,11 +367,24 @@ static int sparse_grid(const b200_ctx* ctx, const HystParams& p) {
     return (int)b;
 }
 
+// <<<grid, 256, 0, st>>> or, for the latency path, the same launch with the programmatic-stream-serialization attribute
+static cudaError_t launch_list_kernel(void (*kernel)(const HystParams), int grid, cudaStream_t st, const HystParams& p) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = p.pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, p);
+}
+
 int launch_ccl_label(b200_ctx* ctx, cudaStream_t st, const HystParams& p_in) {
     HystParams p = p_in;
     if (p.list) {
         ProfScope ps(ctx, st, 1);
-        ccl_sparse_link_kernel<<<sparse_grid(ctx, p), 256, 0, st>>>(p);
+        CB_CUDA(launch_list_kernel(ccl_sparse_link_kernel, sparse_grid(ctx, p), st, p));
         CB_CUDA(cudaGetLastError());
         ctx->launches++;
         return B200_OK;
@@ -399,7 +421,7 @@ int launch_ccl_resolve(b200_ctx* ctx, cudaStream_t st, const HystParams& p_in) {
     HystParams p = p_in;
     if (p.list) {
         ProfScope ps(ctx, st, 3);
-        ccl_sparse_resolve_kernel<<<sparse_grid(ctx, p), 256, 0, st>>>(p);
+        CB_CUDA(launch_list_kernel(ccl_sparse_resolve_kernel, sparse_grid(ctx, p), st, p));
         CB_CUDA(cudaGetLastError());
         ctx->launches++;
         return B200_OK;

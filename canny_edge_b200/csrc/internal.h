@@ -51,6 +51,8 @@ struct GaussTables {
 struct FrontParams {
     const uint8_t* in;      // first byte of buffer row 0 of frame 0
     long long in_frame_stride;  // bytes between frames in `in`
+    int in_bgr;             // 1: `in` holds interleaved B,G,R bytes (3 per pixel, rows of 3*width bytes, in_frame_stride in BYTES):
+                            // front3's fused-conversion variant (front3_bgr_supports); 0: one gray byte per pixel
     int in_row0;            // global row index of buffer row 0 (0 for whole frames; row0-halo for bands)
     int in_rows;            // rows present in the buffer
     int width;              // image width == pitch of every plane
@@ -124,6 +126,8 @@ struct HystParams {
     //           list_retire_kernel on the tile-based path), which also zeroes ctr[0] and ctr[1] for the next launch
     unsigned int* ctr;
     unsigned int* h_kept;        // mapped pinned host word that receives the entry count (density of the next launch's choice) ...
+    int pdl;                     // list-driven kernels only: launch them with programmatic stream serialization (they are resident and
+                                 // parked on griddepcontrol.wait while their predecessor drains) — the single-frame latency path
     unsigned int kept_prev, kept_thresh;   // ... but only when it moves across the threshold: the host's last view of it and the
                                            // "tile-based labelling above this many weak pixels" bound (a write to host memory at the
                                            // end of every launch measured 1 % of the batch throughput)
@@ -216,11 +220,13 @@ int host_window(float sigma);
 // sparse_out: the kernel produced the weak-pixel list
 int launch_front(b200_ctx* ctx, cudaStream_t st, const FrontParams& p, bool* sparse_out = nullptr);
 int make_input_tensor_map(const FrontParams& p, int box_cols, int box_rows, CUtensorMap_st* tmap, bool* use_tma);
+int make_bgr_tensor_map(const FrontParams& p, int box_words, int box_rows, CUtensorMap_st* tmap);   // 32-bit elements over 3*width-byte rows
 // front2.cu
 bool front2_supports(int radius);
 int launch_front2(b200_ctx* ctx, cudaStream_t st, const FrontParams& p);
 // front3.cu (packed-FP32 blur, half-precision Sobel; the default for the radii it is built for)
 bool front3_supports(int radius);
+bool front3_bgr_supports(const FrontParams& p);   // p.in / width / in_frame_stride / radius allow the fused BGR -> gray staging
 int launch_front3(b200_ctx* ctx, cudaStream_t st, const FrontParams& p);
 // selftest.cu
 int check_div_mode_device(b200_ctx* ctx, float b, float y, float* c, int* mode);

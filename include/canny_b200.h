@@ -149,7 +149,8 @@ int b200_canny_steps(b200_ctx* ctx, const uint8_t* img, float sigma, int min_val
 /* cvtColor(frame, gray, COLOR_BGR2GRAY) + cuda_canny — what the reference's frame loop does per frame (src/main.cpp:113,128),
  * with the colour conversion moved onto the GPU.  bgr: height*width*3 bytes, interleaved B,G,R as cv::Mat stores them.  The
  * gray values are OpenCV's 8-bit fixed-point ones ((B*3735 + G*19235 + R*9798 + 2^14) >> 15), bit for bit.  gray_out may be
- * NULL; when given it receives the height*width gray plane the pipeline ran on. */
+ * NULL (then the front kernel converts while it stages its tiles, see b200_canny_batch_device_bgr); when given it receives the
+ * height*width gray plane the pipeline ran on. */
 int b200_canny_bgr(b200_ctx* ctx, const uint8_t* bgr, float sigma, int min_val, int max_val, int height, int width,
                    uint8_t* gray_out, int16_t* edges);
 /* The conversion alone on DEVICE memory (n_px pixels; d_bgr 3*n_px bytes, d_gray n_px bytes), asynchronous on the
@@ -179,6 +180,14 @@ int b200_canny_batch_host_packed(b200_ctx* ctx, const uint8_t* frames, int n_fra
  * d_frames. */
 int b200_canny_batch_device(b200_ctx* ctx, const uint8_t* d_frames, int n_frames, int height,
                             int width, float sigma, int min_val, int max_val, uint8_t* d_edges);
+
+/* b200_canny_batch_device for frames a decoder left in HBM as interleaved B,G,R (cv::Mat's CV_8UC3 layout; d_bgr: n_frames *
+ * height*width*3 bytes): cvtColor(frame, gray, COLOR_BGR2GRAY) (src/main.cpp:113) happens INSIDE the front kernel, on the
+ * staged tile — no separate conversion pass and no gray plane in HBM — when width % 16 == 0, d_bgr is 16-byte aligned and
+ * sigma's half-window is one of 2, 3, 5, 6, 9 (B200_CANNY_BGR_FUSED=0 turns it off); otherwise each chunk is converted into a
+ * gray scratch plane first.  Same gray values either way (OpenCV's fixed-point ones, see b200_canny_bgr), same edge maps. */
+int b200_canny_batch_device_bgr(b200_ctx* ctx, const uint8_t* d_bgr, int n_frames, int height, int width, float sigma,
+                                int min_val, int max_val, uint8_t* d_edges);
 
 /* The packed form of an edge map — 1 bit per pixel, bit i of byte k <-> pixel 8k+i, ceil(n_px/32)*4 bytes — is what
  * b200_canny_batch_host moves over PCIe.  Both halves are exported for callers that store or ship maps in that form:

@@ -1,10 +1,13 @@
 """The two pieces either side of the hot path that SURVEY 8(f) marks "next": BGR->gray on the device (the reference does
 cvtColor on the host, src/main.cpp:113) and a file front end with the reference CLI's arguments (src/main.cpp:29-76)."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
 import canny_edge_b200 as cb
 from canny_edge_b200 import cli
+from canny_edge_b200._lib import check
 
 
 def test_cli_argument_validation_mirrors_main_cpp():
@@ -41,6 +44,58 @@ def test_canny_bgr_matches_cvtcolor_plus_oracle(gpu_ctx, oracle):
         want_gray = cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY)
         assert (gray == want_gray).all() and (gray == gray_formula(frame)).all()
         assert (edges == oracle.canny(want_gray, 1.4, 20, 60)).all()
+
+
+def _colour_frames(n, h, w, seed):
+    rng = np.random.default_rng(seed)
+    gray0 = cb.synth_host(n, h, w, kind=0, seed=seed).astype(np.int16)
+    return np.stack([np.clip(gray0 + rng.integers(-40, 41, (n, h, w)), 0, 255) for _ in range(3)], axis=-1).astype(np.uint8)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sigma", [0.5, 1.4, 2.0, 3.0])
+def test_fused_bgr_front_kernel_matches_cvtcolor_plus_oracle(gpu_ctx, oracle, sigma, monkeypatch):
+    """b200_canny_batch_device_bgr: BGR -> gray inside the front kernel's staging.  Shapes that take the fused
+    kernel (width % 16 == 0; half-windows 2, 5, 6, 9), shapes that cannot (ragged width), strips at both image borders, bands of
+    several slabs, more frames than one chunk; every map against cvtColor + the oracle."""
+    import torch
+    cv2 = pytest.importorskip("cv2")
+    for n, h, w in ((1, 64, 64), (3, 200, 272), (2, 333, 1040), (1, 1080, 1920), (2, 97, 250), (11, 70, 128)):
+        frames = _colour_frames(n, h, w, seed=h + n)
+        d_in = torch.from_numpy(frames).cuda()
+        d_out = torch.empty((n, h, w), dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        gpu_ctx.set_chunk_frames(4 if n > 4 else 0)
+        fast0, gen0 = gpu_ctx.front_kernel_stats()
+        cb.canny_batch_device_bgr_ptr(gpu_ctx, d_in.data_ptr(), n, h, w, sigma, 20, 60, d_out.data_ptr())
+        gpu_ctx.synchronize()
+        gpu_ctx.set_chunk_frames(0)
+        got = d_out.cpu().numpy()
+        for f in range(n):
+            gray = cv2.cvtColor(frames[f], cv2.COLOR_BGR2GRAY)
+            assert (gray == gray_formula(frames[f])).all()
+            want = oracle.canny(gray, sigma, 20, 60)
+            assert (got[f].astype(np.int16) == want).all(), f"{n}x{h}x{w} sigma {sigma} frame {f}: {(got[f] != want).sum()} px differ"
+        assert gpu_ctx.front_kernel_stats()[1] == gen0           # never the generic kernel
+
+
+@pytest.mark.gpu
+def test_fused_bgr_equals_separate_conversion(gpu_ctx, monkeypatch):
+    """Full 4K frames: the fused kernel and (conversion pass + gray kernel) give the same bytes."""
+    import torch
+    n, h, w = 3, 2160, 3840
+    frames = _colour_frames(n, h, w, seed=5)
+    d_in = torch.from_numpy(frames).cuda()
+    d_fused = torch.empty((n, h, w), dtype=torch.uint8, device="cuda")
+    d_gray = torch.empty((n, h, w), dtype=torch.uint8, device="cuda")
+    d_sep = torch.empty((n, h, w), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    cb.canny_batch_device_bgr_ptr(gpu_ctx, d_in.data_ptr(), n, h, w, 1.4, 20, 60, d_fused.data_ptr())
+    check(cb.load().b200_bgr_to_gray_device(gpu_ctx.handle, C.c_void_p(d_in.data_ptr()), n * h * w, C.c_void_p(d_gray.data_ptr())))
+    cb.canny_batch_device_ptr(gpu_ctx, d_gray.data_ptr(), n, h, w, 1.4, 20, 60, d_sep.data_ptr())
+    gpu_ctx.synchronize()
+    assert torch.equal(d_fused, d_sep)
+    assert int((d_fused == 255).sum()) > 10000
 
 
 @pytest.mark.gpu

@@ -51,6 +51,68 @@ __global__ void probe(const float* w, float* out, long long* cycles, int iters) 
     if (a + b + totals == 12345.f) out[0] = a;
 }
 
+// The FMA + guard-band alternative (SURVEY 7 hard part #2) for the same column run: one FFMA2 chain per output (no rounding of the
+// products, so no sharing between symmetric taps), the quotient, and the guard test — the fast result may only be used when the
+// quotient is at least `delta` away from the next integer on either side, otherwise the exact run has to be repeated for that
+// output.  MODE 0: chain only (upper bound of the gain); MODE 1: chain + guard test + vote (no output ever takes the slow path here,
+// which is the best case: flat image regions put EVERY quotient on an integer).
+template <int R, int S, int MODE>
+__global__ void probe_fma(const float* w, float* out, long long* cycles, int iters) {
+    extern __shared__ float sm[];
+    for (int i = threadIdx.x; i < 132 * (S + 2 * R); i += blockDim.x) sm[i] = 1.37f + 0.61f * (i % 7);
+    __syncthreads();
+    u64 ws2[2 * R + 1];
+#pragma unroll
+    for (int j = 0; j <= 2 * R; ++j) ws2[j] = pack2(w[j], w[j]);
+    const float* tcol = sm + 2 * (threadIdx.x & 63);
+    const u64 kBias2 = pack2(8388608.0f, 8388608.0f), kNegBias2 = pack2(-8388608.0f, -8388608.0f), kNegOne = pack2(-1.f, -1.f);
+    u64 total = 0;
+    unsigned slow = 0;
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+        asm volatile("" ::: "memory");
+        u64 x[S + 2 * R];
+#pragma unroll
+        for (int i = 0; i < S + 2 * R; ++i) x[i] = *reinterpret_cast<const u64*>(tcol + i * 132);
+#pragma unroll
+        for (int o = 0; o < S; ++o) {
+            u64 acc = mul2_ftz(x[o], ws2[0]);
+#pragma unroll
+            for (int t = 1; t <= 2 * R; ++t) acc = fma2(x[o + t], ws2[t], acc);
+            const u64 q = fma2(acc, kNegOne, acc);   // stands in for the one-instruction division
+            if (MODE == 1) {
+                const u64 tr = add2(add2_rz(acc, kBias2), kNegBias2);   // trunc
+                float f0, f1;
+                unpack2(add2(acc, fma2(tr, kNegOne, pack2(0.f, 0.f))), f0, f1);   // fractional parts
+                const bool band = (f0 < 1e-3f) | (f0 > 0.999f) | (f1 < 1e-3f) | (f1 > 0.999f);
+                slow |= __ballot_sync(0xffffffffu, band);
+                total = add2(total, tr);
+            } else {
+                total = add2(total, q);
+            }
+        }
+    }
+    long long t1 = clock64();
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+    float a, b;
+    unpack2(total, a, b);
+    if (a + b == 12345.f || slow == 0x12345u) out[0] = a;
+}
+
+template <int R, int S, int MODE>
+void run_fma(const char* name, int warps, const float* dw, float* dout, long long* dcyc, int sms) {
+    const int iters = 200;
+    const size_t smem = 132 * (S + 2 * R) * 4;
+    probe_fma<R, S, MODE><<<sms, 32 * warps, smem>>>(dw, dout, dcyc, iters);
+    cudaDeviceSynchronize();
+    long long h[256];
+    cudaMemcpy(h, dcyc, sizeof(long long) * sms, cudaMemcpyDeviceToHost);
+    double avg = 0;
+    for (int i = 0; i < sms; ++i) avg += h[i];
+    avg /= sms;
+    printf("%-28s warps/SM %2d (per scheduler %d): %8.0f clk per block\n", name, warps, warps / 4, avg);
+}
+
 template <int R, int S, bool SCALAR>
 void run(const char* name, int warps, const float* dw, float* dout, long long* dcyc, int sms) {
     const int iters = 200;
@@ -81,5 +143,7 @@ int main() {
     for (int warps : {4, 8, 16, 32}) run<5, 18, false>("packed S=18", warps, dw, dout, dcyc, sms);
     for (int warps : {4, 8, 16}) run<5, 34, false>("packed S=34", warps, dw, dout, dcyc, sms);
     for (int warps : {4, 8, 16, 32}) run<5, 34, true>("scalar S=34", warps, dw, dout, dcyc, sms);
+    for (int warps : {4, 8, 16, 32}) run_fma<5, 18, 0>("fma chain S=18", warps, dw, dout, dcyc, sms);
+    for (int warps : {4, 8, 16, 32}) run_fma<5, 18, 1>("fma chain + guard S=18", warps, dw, dout, dcyc, sms);
     return 0;
 }

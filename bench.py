@@ -16,6 +16,7 @@ NMS -> hysteresis) over the rank's frames.
                 the three-stream production run (they share SMs with the previous chunk's hysteresis kernels and each other's tails).
   content       device-resident Mpix/s of 64-frame batches of the three input families (shapes / tiled tests/test.jpg / noise).
   parity        GPU edge maps of the CPU sample's frames compared with the reference CPU path's, pixel by pixel.
+  bgr           interleaved B,G,R frames in HBM (the reference's cvtColor step, src/main.cpp:113): converted inside the front kernel.
   latency       BASELINE configs[1]: one 1920x1080 frame, device-resident and through the host API.
   bands         BASELINE configs[4]: ONE 32768x32768 image row-band sharded over the N GPUs through the C handle (b200_bands_*):
                 halo rows pulled over NVLink by the copy engines, boundary-record exchange, cross-band hysteresis merge; strong
@@ -495,6 +496,28 @@ def run_b200(a, rank, world, local_rank):
             content[name] = {"value": round(world * nc * h * w * 5 / (cms * 1e-3) / 1e6, 1), "edge_fraction": round(cnt.value / (nc * h * w), 5)}
         out["content"] = {"unit": "Mpix/s", "frames_per_gpu": nc, "families": content,
                           "note": "the headline generator (shapes) is the sparsest of the three; photographs behave like testjpg_tiled"}
+
+        # ---- interleaved B,G,R input (cvtColor(BGR2GRAY), src/main.cpp:113, folded into the front kernel's staging) ----
+        if hasattr(lib, "b200_canny_batch_device_bgr") and n_buf >= 8:
+            nb = min(32, n_buf // 4)
+            check(lib.b200_synth_device(ctx.handle, d_in.data_ptr(), nb, h, w, 0, 1234, rank * nb))
+            torch.cuda.synchronize()
+            bgr = d_in[nb:4 * nb].view(nb, h, w, 3)                        # colour frames whose gray value stays close to the synthetic frame
+            for ch, delta in enumerate((-9, 3, -4)):
+                bgr[..., ch] = (d_in[:nb].to(torch.int16) + delta).clamp_(0, 255).to(torch.uint8)
+            gray = d_out[nb:2 * nb]
+            m_fused, m_gray = d_out[:nb], d_out[2 * nb:3 * nb]
+            torch.cuda.synchronize()
+            conv_ms = env.timed(lambda: check(lib.b200_bgr_to_gray_device(ctx.handle, bgr.data_ptr(), nb * h * w, gray.data_ptr())), 5, 2) / 5
+            gms = env.timed(lambda: cb.canny_batch_device_ptr(ctx, gray.data_ptr(), nb, h, w, SIGMA, LO, HI, m_gray.data_ptr()), 5, 2) / 5
+            fms = env.timed(lambda: cb.canny_batch_device_bgr_ptr(ctx, bgr.data_ptr(), nb, h, w, SIGMA, LO, HI, m_fused.data_ptr()), 5, 2) / 5
+            rate = lambda ms_: round(world * nb * h * w / (ms_ * 1e-3) / 1e6, 1)
+            out["bgr"] = {"unit": "Mpix/s", "frames_per_gpu": nb, "fused": rate(fms), "gray_input": rate(gms),
+                          "separate_pass": rate(gms + conv_ms), "conversion_pass_alone_ms": round(conv_ms, 4),
+                          "maps_equal": bool(torch.equal(m_fused, m_gray)),
+                          "note": "b200_canny_batch_device_bgr: device-resident interleaved B,G,R frames; fused = converted while the front kernel "
+                                  "stages its tiles (no gray plane in HBM); separate_pass = the 4 B/px conversion kernel followed by the gray "
+                                  "pipeline (serial sum of the two measured times); gray values are OpenCV's fixed-point ones either way"}
 
         # ---- latency configuration: BASELINE configs[1], one 1920x1080 frame ----
         lh, lw = 1080, 1920

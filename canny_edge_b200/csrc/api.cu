@@ -318,8 +318,10 @@ static int check_thresholds(int lo, int hi) {
 
 // Runs front + hysteresis on device-resident frames [f0, f0+nf) using workspace slot `slot` on stream st.
 // bgr: d_in holds interleaved B,G,R frames (3 bytes per pixel) and the front kernel converts while staging (front3_bgr_supports)
+// bands_hint > 0: row bands per frame for the front kernel's grid (0: the launcher's own choice)
 static int run_frames_device(b200_ctx* ctx, cudaStream_t st, int slot, const uint8_t* d_in, uint8_t* d_out, int nf, int h,
-                             int w, int lo, int hi, int16_t* blur, int16_t* mag, int16_t* ang, int16_t* nms, bool bgr = false) {
+                             int w, int lo, int hi, int16_t* blur, int16_t* mag, int16_t* ang, int16_t* nms, bool bgr = false,
+                             int bands_hint = 0) {
     const long long px = (long long)h * w;
     FrontParams fp;
     memset(&fp, 0, sizeof(fp));
@@ -327,6 +329,7 @@ static int run_frames_device(b200_ctx* ctx, cudaStream_t st, int slot, const uin
     fp.in_row0 = 0; fp.in_rows = h; fp.width = w; fp.height = h;
     fp.out_row0 = 0; fp.out_rows = h; fp.n_frames = nf; fp.cls = d_out; fp.out_frame_stride = px;
     fp.blur = blur; fp.mag = mag; fp.ang = ang; fp.nms = nms;
+    fp.tiles_y = bands_hint;
     fp.w = ctx->gauss.d_w; fp.count = ctx->gauss.d_count; fp.radius = ctx->gauss.radius;
     fill_thresholds(fp, lo, hi);
     // sparse hand-over to hysteresis (used when the lean front kernel runs): union-find slots + weak-pixel list
@@ -813,7 +816,14 @@ static int batch_device_impl(b200_ctx* ctx, const uint8_t* d_frames, int n_frame
             CB_TRY(launch_bgr_to_gray(ctx, st, src, gray, (size_t)px * (size_t)nf));
             src = gray;
         }
-        return run_frames_device(ctx, st, s, src, d_edges + (long long)f0 * px, nf, h, w, lo, hi, nullptr, nullptr, nullptr, nullptr, fused);
+        // The last full chunk of a call is cut into four row bands per frame: a front CTA otherwise marches a whole strip of a frame
+        // (0.3 ms at 4K) and the call ends with SMs idling while the last of those finish.  Measured on 64-frame calls (one GPU's
+        // share of the 512-frame job at 8 GPUs): 2.118 -> 2.075 ms; 512-frame calls unchanged (tools/chunk_sweep.py).
+        static const int tail_bands = [] { const char* e = getenv("B200_CANNY_TAIL_BANDS"); return e ? atoi(e) : 4; }();
+        static const int tail_chunks = [] { const char* e = getenv("B200_CANNY_TAIL_CHUNKS"); return e ? atoi(e) : 1; }();
+        int bands = 0;
+        if (n_chunks > 1 && f0 + nf > n_frames - tail_chunks * chunk && nf == chunk && tail_bands > 1 && h / tail_bands >= 256) bands = tail_bands;
+        return run_frames_device(ctx, st, s, src, d_edges + (long long)f0 * px, nf, h, w, lo, hi, nullptr, nullptr, nullptr, nullptr, fused, bands);
     };
     if (n_slots == 1) return run_chunk(ctx->stream, 0, 0, n_frames);
     // the side streams take the chunks in turn so one chunk's tail waves overlap the next chunks' heads

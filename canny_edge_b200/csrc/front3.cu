@@ -158,7 +158,9 @@ front3_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
     const int lane = tid & 31, warp = tid >> 5;
     // latency path: the list-driven hysteresis kernel behind this one may be launched programmatically (HystParams::pdl); it parks
     // on griddepcontrol.wait until this grid has completed.  A no-op for ordinary launches.
+#ifndef F3_NO_PDL_TRIGGER
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
 
     // ---- which strip / band / frame ----
     const int strip = blockIdx.x, band = blockIdx.y, frame = blockIdx.z;

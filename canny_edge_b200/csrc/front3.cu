@@ -691,8 +691,10 @@ front3_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
             pend_base = 0;
             // (inline PTX: nvcc turns a plain atomicAdd in divergent code into its warp-aggregated form, whose shuffle needs the
             // atomic's result at once — 2 % of the kernel's warp-time waited on that round trip)
+            // ptxas does the same to a PTX atom on an address it can prove uniform, so the address carries threadIdx.z (always 0,
+            // but a per-thread value)
             if (total && lane == 0)
-                asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(pend_base) : "l"(p.kept_count), "r"((unsigned int)total) : "memory");
+                asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(pend_base) : "l"(p.kept_count + threadIdx.z), "r"((unsigned int)total) : "memory");
             pend_off = incl - cnt;
             // word tid <-> class row rr = tid >> 2, columns 32*(tid & 3) .. of the strip
             pend_g0 = (int)((long long)frame * p.out_frame_stride + (long long)(y_base + (tid >> 2) - p.plane_row0) * W + x0 + 32 * (tid & 3));

@@ -511,9 +511,7 @@ front3_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
         // them are neighbour-only rows and may lie outside the image
         const int cq_lo = max(1, yb - y_base + 1), cq_hi = min(kSlab, ye - y_base);
         {
-            auto n_of_row = [&](const int32_t* vrow) -> float4 {
-                const uint4 qa = *reinterpret_cast<const uint4*>(vrow);
-                const uint2 qb = *reinterpret_cast<const uint2*>(vrow + 4);
+            auto n_of_words = [&](const uint4 qa, const uint2 qb) -> float4 {
                 const uint32_t wd[6] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y};
                 float nv[4];
 #pragma unroll
@@ -526,6 +524,9 @@ front3_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
                     }
                 }
                 return make_float4(nv[0], nv[1], nv[2], nv[3]);
+            };
+            auto n_of_row = [&](const int32_t* vrow) -> float4 {
+                return n_of_words(*reinterpret_cast<const uint4*>(vrow), *reinterpret_cast<const uint2*>(vrow + 4));
             };
             if (cq_lo <= cq_hi) {
                 // the two neighbour-only rows: warps 0 and 1
@@ -548,8 +549,7 @@ front3_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
                 const long long o_step = 8LL * W;
                 // two copies of the loop so the store form is decided once, not per row: the aligned 32-bit store (every strip of
                 // an image whose width is a multiple of 4, except a ragged last strip) or byte stores
-                auto class_row = [&](const int32_t* vr, float* nr, int e16) {
-                    const float4 nq = n_of_row(vr);
+                auto class_row_nq = [&](const float4 nq, float* nr, int e16) {
                     *reinterpret_cast<float4*>(nr) = nq;
                     // one entry per PAIR of pixels (columns 4*lane+1.. +2 and 4*lane+3.. +4) that holds a candidate: candidates
                     // come in bands a few pixels wide, so pairs leave fewer idle pixel slots in phase 3b than whole quads
@@ -560,14 +560,27 @@ front3_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
                     if (any_hi) my_ent[my_count + n_lo + __popc(vote_hi & lt_mask)] = (uint16_t)(e16 | 1);
                     my_count += n_lo + __popc(vote_hi);
                 };
+                auto class_row = [&](const int32_t* vr, float* nr, int e16) { class_row_nq(n_of_row(vr), nr, e16); };
                 // every class word starts out as "suppressed"; phase 3b overwrites the bytes of surviving pixels
                 if (cq_lo == 1 && cq_hi == kSlab && ((W & 3) == 0)) {
                     // the common slab (all 64 class rows, image width a multiple of 4): the warp's eight rows unrolled, every address an
                     // immediate offset from the first row's (word_ok is false for the columns past a ragged right edge)
+                    // The next row's Sobel words are fetched before this row's stores: the compiler cannot move a shared-memory load
+                    // above the n-plane / list stores of the row before (it cannot prove they do not alias), and every row would
+                    // otherwise start by waiting for its own loads.
+                    uint4 qa = *reinterpret_cast<const uint4*>(vrow);
+                    uint2 qb = *reinterpret_cast<const uint2*>(vrow + 4);
 #pragma unroll
                     for (int i = 0; i < kSlab / 8; ++i) {
-                        class_row(vrow + 8 * i * kVuPitch, nrow + 8 * i * kNpPitch, ent + ((8 * i) << 6));
+                        uint4 qa_next = qa;
+                        uint2 qb_next = qb;
+                        if (i + 1 < kSlab / 8) {
+                            qa_next = *reinterpret_cast<const uint4*>(vrow + 8 * (i + 1) * kVuPitch);
+                            qb_next = *reinterpret_cast<const uint2*>(vrow + 8 * (i + 1) * kVuPitch + 4);
+                        }
+                        class_row_nq(n_of_words(qa, qb), nrow + 8 * i * kNpPitch, ent + ((8 * i) << 6));
                         if (word_ok) *reinterpret_cast<uint32_t*>(o + i * o_step) = zero_word;
+                        qa = qa_next; qb = qb_next;
                     }
                 } else if (__all_sync(0xffffffffu, word_ok || lane >= kTW / 4)) {
                     for (; q <= cq_hi; q += 8, vrow += 8 * kVuPitch, nrow += 8 * kNpPitch, o += o_step, ent += 8 << 6) {
@@ -789,7 +802,9 @@ static int choose_bands3(const b200_ctx* ctx, int out_rows, int strips, int fram
     const long long per_band = (long long)strips * frames;
     int best = 1;
     double best_cost = 1e300;
-    const int max_bands = out_rows / 64 > 0 ? out_rows / 64 : 1;
+    // bands down to 32 rows: a 256-row frame cut into 6 bands is ONE slab per CTA (43 + 2R + 4 rows) instead of two (256 x 256 frame:
+    // 34 -> 26 us); large frames never get there (more CTAs than slots means more waves)
+    const int max_bands = out_rows / 32 > 0 ? out_rows / 32 : 1;
     for (int b = 1; b <= max_bands && b <= 64; ++b) {
         const int rows = (out_rows + b - 1) / b;
         const int slabs = (rows + 2 * radius + 4 + slab - 1) / slab;
@@ -810,6 +825,8 @@ int launch_front3(b200_ctx* ctx, cudaStream_t st, const FrontParams& p_in) {
     // busy instead of 63 %) but then executes 19 % more instructions (shorter runs share fewer products, twice the tail copies and
     // per-slab set-up) and ends up 2-3 % slower on the 4K batch, so only the 64-row form is instantiated.
     constexpr int slab = 64;
+    static const int bands_env = [] { const char* e = getenv("B200_CANNY_BANDS"); return e ? atoi(e) : 0; }();   // experiments
+    if (p.tiles_y <= 0 && bands_env > 0 && p.out_rows / bands_env >= 1) p.tiles_y = bands_env;
     if (p.tiles_y <= 0) p.tiles_y = choose_bands3(ctx, p.out_rows, strips, p.n_frames, radius, slab);
     dim3 grid(strips, p.tiles_y, p.n_frames);
     CUtensorMap tmap;

@@ -66,6 +66,13 @@ for tag, frames in (("9f", 9), ("4f", 4)):
             "algorithmic_bytes_per_launch": 2 * px}, indent=1) + "\n")
         print("front traffic", traffic, traffic / px)
 
+# ---- the fused-BGR variant (9 interleaved B,G,R frames) ----
+if (G / "r02_front3_bgr_9f.ncu-rep").exists():
+    lines, recs = summarise(G / "r02_front3_bgr_9f.ncu-rep",
+                            "ncu --set full --import-source on --clock-control none -k regex:front3_kernel -s 5 -c 1 python tools/bgr_probe.py --frames 9: "
+                            "front3_kernel<5,TMA,DIV=1,64,BGR>, one launch of 9 interleaved B,G,R frames 3840x2160 (4 B/px algorithmic: 3 in + 1 out)")
+    (P / "r02_front3_bgr_9f_ncu_full.txt").write_text("\n".join(lines) + "\n")
+
 # ---- hysteresis kernels: in the pipeline (caches not flushed) vs cold ----
 for tag, title in (("inpipe", "--cache-control none: what the kernels read was just written by the front kernel of the same chunk (27 frames = 3 chunks in flight)"),
                    ("cold", "default cache control (flushed before every replay): round 1's view")):
@@ -110,11 +117,26 @@ for n in (2, 8):
             keep = [l for l in src.read_text().splitlines() if l.startswith("{")]
             (P / f"r02_multigpu_bands_{tag}_n{n}.jsonl").write_text("\n".join(keep) + "\n")
 
+# ---- probes ----
+for src, dst in (("r02_chunk_sweep.txt", "r02_chunk_sweep.txt"), ("r02_pytest_gpu.log", "r02_pytest_gpu.log")):
+    if (G / src).exists():
+        shutil.copy(G / src, P / dst)
+probe = {}
+for name in ("bgr_fused", "bgr_separate", "bgr8k_fused", "bgr8k_separate", "pdl0", "pdl1"):
+    f = G / f"r02_{name}.json"
+    if f.exists():
+        try:
+            probe[name] = json.loads(f.read_text().strip().splitlines()[-1])
+        except Exception as e:
+            probe[name] = {"error": str(e)}
+if probe:
+    (P / "r02_bgr_pdl_probes.json").write_text(json.dumps(probe, indent=1) + "\n")
+
 # ---- SASS evidence ----
-sass = subprocess.run([sys.executable, str(ROOT / "tools" / "sass_check.py"), "front3_kernelILi5ELb1ELi1ELi64"], capture_output=True, text=True).stdout
+sass = subprocess.run([sys.executable, str(ROOT / "tools" / "sass_check.py"), "front3_kernelILi5ELb1ELi1ELi64ELb0"], capture_output=True, text=True).stdout
 (P / "r02_front3_sass_summary.txt").write_text(sass)
 lib = ROOT / "canny_edge_b200" / "libcanny_b200.so"
-full = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN2cb2f313front3_kernelILi5ELb1ELi1ELi64EEEvNS_11FrontParamsE14CUtensorMap_st", str(lib)],
+full = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN2cb2f313front3_kernelILi5ELb1ELi1ELi64ELb0EEEvNS_11FrontParamsE14CUtensorMap_st", str(lib)],
                       capture_output=True, text=True).stdout
 keep = []
 for line in full.splitlines():

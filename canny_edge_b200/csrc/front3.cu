@@ -122,7 +122,10 @@ __device__ __forceinline__ void red_or_shared_if(bool on, uint32_t* ptr, uint32_
 // resident next to them instead of waiting for a front CTA to retire: the front kernel alone gets 1.7 % slower, the chunk
 // pipeline 2.3 % faster on the bench frames and 8 % faster on photographic content (112 / 104 / 88 / 80 measured too: 96 wins).
 template <int R, bool USE_TMA, int DIV, int SLAB, bool BGR = false>
-__global__ void __maxnreg__(SLAB == 64 ? 96 : 64)
+#ifndef F3_MAXREG
+#define F3_MAXREG 96
+#endif
+__global__ void __maxnreg__(SLAB == 64 ? F3_MAXREG : 64)
 front3_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int kSlab = SLAB;

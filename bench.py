@@ -450,7 +450,22 @@ def run_b200(a, rank, world, local_rank):
         t0 = time.perf_counter()
         h_out.copy_(h_in)
         host_copy_gbs = 2 * px_e / (time.perf_counter() - t0) / 1e9
+        # ... and what PCIe gives it: plain pinned H2D copies of the same input batch (all ranks at once, like the e2e run itself)
+        env.barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nce = min(ne, n_buf)
+        d_in[:nce].copy_(h_in[:nce], non_blocking=True)
+        c0.record()
+        for _ in range(3):
+            d_in[:nce].copy_(h_in[:nce], non_blocking=True)
+        c1.record()
+        env.barrier()
+        pcie_h2d_gbs = 3 * nce * h * w / (env.max_over_ranks(c0.elapsed_time(c1)) * 1e-3) / 1e9
         e2e = e2e_leg(lambda: check(lib.b200_canny_batch_host(ctx.handle, h_in.data_ptr(), ne, h, w, C.c_float(SIGMA), LO, HI, h_out.data_ptr())))
+        e2e["pcie"] = {"h2d_copy_gbs_per_gpu": round(pcie_h2d_gbs, 1), "e2e_input_gbs_per_gpu": round(e2e["value"] / world / 1e3, 1),
+                       "frac_of_h2d_copy": round(e2e["value"] / world / 1e3 / pcie_h2d_gbs, 3),
+                       "note": "the e2e run moves 1 B/px in (and 1/8 B/px out, the other direction): its Gpix/s per GPU against the rate of plain pinned "
+                               "H2D copies of the same frames is how close the host path is to the PCIe ceiling"}
         e2e["host"] = {"numa_node_bound": env.numa_node, "pinned_copy_gbs_one_thread": round(host_copy_gbs, 1), "cpus_visible": len(os.sched_getaffinity(0)),
                        "note": "every rank's frames and maps cross the same host memory system and PCIe root complexes: the e2e figure stops scaling "
                                "where they saturate; the packed form moves 1/8 of the map bytes through host DRAM and no expansion pass"}

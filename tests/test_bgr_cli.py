@@ -80,6 +80,18 @@ def test_fused_bgr_front_kernel_matches_cvtcolor_plus_oracle(gpu_ctx, oracle, si
 
 
 @pytest.mark.gpu
+def test_canny_bgr_without_gray_plane_takes_the_fused_kernel(gpu_ctx, oracle):
+    """b200_canny_bgr with gray_out == NULL: host B,G,R frame in, int16 map out, conversion inside the front kernel where the width
+    allows (640, 1920) and through the conversion kernel where it does not (641)."""
+    cv2 = pytest.importorskip("cv2")
+    for h, w in ((480, 640), (480, 641), (1080, 1920)):
+        frame = _colour_frames(1, h, w, seed=w)[0]
+        edges = cb.cuda_canny_bgr(frame, 1.4, 20, 60, ctx=gpu_ctx)
+        want = oracle.canny(cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY), 1.4, 20, 60)
+        assert (edges == want).all(), f"{h}x{w}: {(edges != want).sum()} px differ"
+
+
+@pytest.mark.gpu
 def test_fused_bgr_equals_separate_conversion(gpu_ctx, monkeypatch):
     """Full 4K frames: the fused kernel and (conversion pass + gray kernel) give the same bytes."""
     import torch

@@ -253,11 +253,13 @@ front3_kernel(const FrontParams p, const __grid_constant__ CUtensorMap tmap) {
             return __byte_perm(__byte_perm(g0, g1, 0x0062), __byte_perm(g2, g3, 0x0062), 0x5410);
         };
         constexpr int kHU = 20;
-        static_assert((kSlab * kHU) % kThreads == 0, "whole rounds");
+        static_assert((kSlab * kHU) % kThreads == 0 && kSlab * 16 % kThreads == 0 && kSlab * 4 == kThreads, "whole rounds");
 #pragma unroll
         for (int t0 = 0; t0 < kSlab * kHU; t0 += kThreads) {
-            const int t = t0 + tid;
-            const int r = t / kHU, hu = t - r * kHU;
+            // tasks 0..15 of a row belong to one half-warp (24 B apart: its 64-bit loads touch every bank once); the four left over
+            // per row make up the last round
+            const int r = t0 < kSlab * 16 ? (t0 + tid) >> 4 : tid >> 2;
+            const int hu = t0 < kSlab * 16 ? (tid & 15) : 16 + (tid & 3);
             const uint2* src = reinterpret_cast<const uint2*>(s_bgr + r * (3 * in_pitch) + hu * 24);
             const uint2 a = src[0], b = src[1], c = src[2];
             *reinterpret_cast<uint2*>(s_in + r * in_pitch + hu * 8) = make_uint2(gray4(a.x, a.y, b.x), gray4(b.y, c.x, c.y));

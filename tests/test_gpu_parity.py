@@ -294,6 +294,28 @@ def test_device_batch_and_synth_match_host(gpu_ctx, oracle):
     assert cnt.value == int((got == 255).sum())
 
 
+def test_device_batch_tail_chunk_in_row_bands(gpu_ctx, oracle):
+    """The last full chunk of a device batch is launched with four row bands per frame (shorter CTAs at the end of a call): frames
+    tall enough for that (height / 4 >= 256), several chunks, a remainder chunk; every frame against the oracle."""
+    import torch
+    n, h, w = 5, 1100, 640
+    host = cb.synth_host(n, h, w, kind=1, seed=99)
+    host[1] = cb.synth_host(1, h, w, kind=0, seed=5)[0]
+    host[3] = cb.synth_host(1, h, w, kind=0, seed=6)[0]
+    d_in = torch.from_numpy(host).cuda()
+    d_out = torch.empty_like(d_in)
+    torch.cuda.synchronize()
+    gpu_ctx.set_chunk_frames(2)          # chunks of 2, 2 (the banded one) and 1 frame
+    try:
+        cb.canny_batch_device_ptr(gpu_ctx, d_in.data_ptr(), n, h, w, 1.4, 20, 60, d_out.data_ptr())
+        gpu_ctx.synchronize()
+    finally:
+        gpu_ctx.set_chunk_frames(0)
+    got = d_out.cpu().numpy()
+    for f in range(n):
+        assert_same(f"frame {f}", got[f].astype(np.int16), oracle.canny(host[f], 1.4, 20, 60))
+
+
 @pytest.mark.parametrize("h,w,sigma,kind", [(1080, 1920, 1.4, 0), (1080, 1920, 1.4, 1), (2160, 3840, 1.4, 0), (1024, 1024, 5.0, 0)])
 def test_full_size_vs_oracle(gpu_ctx, oracle, h, w, sigma, kind):
     # BASELINE configs 2-4 at (or near) full size: the oracle still finishes in seconds here
